@@ -1,0 +1,184 @@
+"""Deterministic synthetic inputs (the JVET sequences and the trained MSBD weights are
+not available offline): YUV 4:2:0 10-bit frames of the VVC class shapes, seeded
+weights with the reference's parameter names, and structured partition maps for
+decode-only tests and benches."""
+from collections import OrderedDict
+
+import numpy as np
+
+from .netspec import param_spec
+
+# /root/reference/VVC_Test_Sequences.txt class shapes
+CLASS_SHAPES = {"D": (416, 240), "C": (832, 480), "B": (1920, 1080), "A": (3840, 2160)}
+
+
+def _bilinear_up(grid, h, w):
+    gh, gw = grid.shape
+    ys = np.linspace(0, gh - 1, h)
+    xs = np.linspace(0, gw - 1, w)
+    y0 = np.minimum(ys.astype(np.int64), gh - 2)
+    x0 = np.minimum(xs.astype(np.int64), gw - 2)
+    fy = (ys - y0)[:, None]
+    fx = (xs - x0)[None, :]
+    g00 = grid[y0][:, x0]
+    g01 = grid[y0][:, x0 + 1]
+    g10 = grid[y0 + 1][:, x0]
+    g11 = grid[y0 + 1][:, x0 + 1]
+    return (g00 * (1 - fx) + g01 * fx) * (1 - fy) + (g10 * (1 - fx) + g11 * fx) * fy
+
+
+def _plane(rng, h, w, base, amp, n_patches, noise):
+    img = np.full((h, w), base, dtype=np.float64)
+    for scale, a in ((96, 1.0), (32, 0.5), (12, 0.25)):
+        gh, gw = h // scale + 2, w // scale + 2
+        img += amp * a * _bilinear_up(rng.standard_normal((gh, gw)), h, w)
+    yy, xx = np.mgrid[0:h, 0:w]
+    for _ in range(n_patches):
+        ph = int(rng.integers(8, max(9, min(h, 192))))
+        pw = int(rng.integers(8, max(9, min(w, 192))))
+        py = int(rng.integers(0, h - ph + 1))
+        px = int(rng.integers(0, w - pw + 1))
+        kind = int(rng.integers(0, 3))
+        sl = (slice(py, py + ph), slice(px, px + pw))
+        if kind == 0:      # oriented sinusoid
+            th = rng.uniform(0, np.pi)
+            per = rng.uniform(4, 40)
+            ph0 = rng.uniform(0, 2 * np.pi)
+            img[sl] += rng.uniform(5, 40) * np.sin(
+                2 * np.pi * (np.cos(th) * xx[sl] + np.sin(th) * yy[sl]) / per + ph0)
+        elif kind == 1:    # flat object with hard edges
+            img[sl] = img[sl] * 0.3 + rng.uniform(20, 230)
+        else:              # oriented ramp / edge
+            th = rng.uniform(0, np.pi)
+            t = np.cos(th) * (xx[sl] - px - pw / 2) + np.sin(th) * (yy[sl] - py - ph / 2)
+            img[sl] += rng.uniform(10, 60) * np.tanh(t / rng.uniform(0.5, 6))
+    img += noise * rng.standard_normal((h, w))
+    return img
+
+
+def synth_yuv420(width, height, frames, seed=0, bitdepth=10):
+    """Planar 4:2:0 frames: y [F,H,W], u/v [F,H/2,W/2]; uint16 (10-bit range) or uint8."""
+    rng = np.random.default_rng([seed, width, height])
+    scale = 4.0 if bitdepth == 10 else 1.0
+    dt = np.uint16 if bitdepth == 10 else np.uint8
+    top = 1023 if bitdepth == 10 else 255
+    ys, us, vs = [], [], []
+    npatch = max(4, (width * height) // (96 * 96))
+    for _ in range(frames):
+        y = _plane(rng, height, width, 118.0, 45.0, npatch, 1.5)
+        u = _plane(rng, height // 2, width // 2, 128.0, 14.0, npatch // 3, 0.8)
+        v = _plane(rng, height // 2, width // 2, 128.0, 14.0, npatch // 3, 0.8)
+        ys.append(np.clip(np.rint(y * scale), 0, top).astype(dt))
+        us.append(np.clip(np.rint(u * scale), 0, top).astype(dt))
+        vs.append(np.clip(np.rint(v * scale), 0, top).astype(dt))
+    return np.stack(ys), np.stack(us), np.stack(vs)
+
+
+def synth_blocks(n, seed=0):
+    """Config-4 style inputs: n 64x64 blocks cut from synthetic frames.
+    Returns block_y [n,68,68], block_u/v [n,34,34] uint8."""
+    rng = np.random.default_rng([seed, n])
+    side = 512
+    per = (side // 64) ** 2
+    nf = (n + per - 1) // per
+    y, u, v = synth_yuv420(side, side, nf, seed=int(rng.integers(1 << 30)), bitdepth=8)
+    by = np.zeros((nf * per, 68, 68), np.uint8)
+    bu = np.zeros((nf * per, 34, 34), np.uint8)
+    bv = np.zeros((nf * per, 34, 34), np.uint8)
+    yp = np.pad(y, ((0, 0), (4, 0), (4, 0)))
+    up = np.pad(u, ((0, 0), (2, 0), (2, 0)))
+    vp = np.pad(v, ((0, 0), (2, 0), (2, 0)))
+    k = 0
+    for f in range(nf):
+        for i in range(side // 64):
+            for j in range(side // 64):
+                by[k] = yp[f, i * 64:i * 64 + 68, j * 64:j * 64 + 68]
+                bu[k] = up[f, i * 32:i * 32 + 34, j * 32:j * 32 + 34]
+                bv[k] = vp[f, i * 32:i * 32 + 34, j * 32:j * 32 + 34]
+                k += 1
+    return by[:n], bu[:n], bv[:n]
+
+
+def seeded_state_dict(net, seed, gain=0.65):
+    """Deterministic weights with the reference's names/shapes (numpy float32 arrays).
+
+    Conv weights ~ U(-b, b), b = gain * sqrt(3 / fan_in) (variance gain^2/fan_in);
+    biases ~ U(-0.1, 0.1); the depth channel of the three MSBD output convs gets a
+    positive bias so cumulative depths straddle the 0.5/1.5/2.5 decision thresholds
+    (gain 0.65 keeps the 30-conv-deep MSBD nets from exploding or collapsing on
+    0..255 pixel inputs: outputs land in about [-4, 4]).
+    Used where the trained *_BD_*.pkl are missing."""
+    rng = np.random.default_rng([seed, sum(map(ord, net))])
+    sd = OrderedDict()
+    for name, shp in param_spec(net):
+        if name.endswith(".bias"):
+            sd[name] = rng.uniform(-0.1, 0.1, size=shp).astype(np.float32)
+            if name in ("conv_B1.bias", "conv_B2.bias", "conv_B3.bias"):
+                sd[name][0] = 0.8 if name == "conv_B1.bias" else 0.5
+        else:
+            fan_in = shp[1] * shp[2] * shp[3]
+            b = gain * np.sqrt(3.0 / fan_in)
+            sd[name] = rng.uniform(-b, b, size=shp).astype(np.float32)
+    return sd
+
+
+# --------------------------------------------------------------------------
+# structured partition maps for decode-only tests / benches
+# --------------------------------------------------------------------------
+def _split(x, y, h, w, m):
+    if m == 1:
+        return [(x, y, h // 2, w), (x + h // 2, y, h // 2, w)]
+    if m == 2:
+        return [(x, y, h, w // 2), (x, y + w // 2, h, w // 2)]
+    if m == 3:
+        return [(x, y, h // 4, w), (x + h // 4, y, h // 2, w), (x + 3 * h // 4, y, h // 4, w)]
+    return [(x, y, h, w // 4), (x, y + w // 4, h, w // 2), (x, y + 3 * w // 4, h, w // 4)]
+
+
+def _legal(h, w, m, cf):
+    ln = h if m in (1, 3) else w
+    unit = (2 if m <= 2 else 4) * cf
+    return ln // unit > 0 and ln % unit == 0
+
+
+def structured_maps(n, seed=0, sigma=0.15, chroma=False, p_split=0.6):
+    """Random legal QT + 3-level MTT partitions rendered to label maps + N(0, sigma) noise.
+
+    Returns (qt [n,8,8] float32 holding ints 0..3, bt [n,3,16,16] f32, dire [n,3,16,16] f32)."""
+    rng = np.random.default_rng([seed, n, int(chroma)])
+    cf = 2 if chroma else 1
+    qt = np.zeros((n, 8, 8), np.float32)
+    bt = np.zeros((n, 3, 16, 16), np.float32)
+    dire = np.zeros((n, 3, 16, 16), np.float32)
+
+    def mtt(b, x, y, h, w, lvl, cur):
+        if lvl == 3:
+            return
+        modes = [m for m in (1, 2, 3, 4) if _legal(h, w, m, cf)]
+        if not modes or rng.random() > p_split:
+            for l in range(lvl, 3):
+                bt[b, l, x:x + h, y:y + w] = cur
+            return
+        m = modes[int(rng.integers(len(modes)))]
+        dire[b, lvl, x:x + h, y:y + w] = 1.0 if m in (1, 3) else -1.0
+        for i, (sx, sy, sh, sw) in enumerate(_split(x, y, h, w, m)):
+            v = cur + (2 if (m >= 3 and i != 1) else 1)
+            bt[b, lvl, sx:sx + sh, sy:sy + sw] = v
+            mtt(b, sx, sy, sh, sw, lvl + 1, v)
+
+    def quad(b, d, qx, qy):
+        size = 8 >> d
+        if d < 3 and rng.random() < (0.55 if d == 0 else 0.4):
+            for io in range(2):
+                for jo in range(2):
+                    quad(b, d + 1, qx + io * size // 2, qy + jo * size // 2)
+        else:
+            qt[b, qx:qx + size, qy:qy + size] = d
+            mtt(b, 2 * qx, 2 * qy, 2 * size, 2 * size, 0, 0)
+
+    for b in range(n):
+        quad(b, 0, 0, 0)
+    if sigma > 0:
+        bt += (sigma * rng.standard_normal(bt.shape)).astype(np.float32)
+        dire += (sigma * rng.standard_normal(dire.shape)).astype(np.float32)
+    return qt, bt, dire
