@@ -1,0 +1,178 @@
+"""Drop-in for the reference driver ``Inference_QBD.py``: same function names and CLI flags
+(``--jobID --inputDir --outDir --batchSize --startSeqID --seqNum``, Inference_QBD.py:257-267), same output tree
+``<outDir>/<jobID>/PartitionMat/<seq>_<comp>_QP<qp>_PartitionMat.txt`` and ``Time_Sta_*.txt``.
+
+The reference hard-codes ``Training_Sequences.txt``, ``.\\per-sequence`` and ``./CTU_Models/`` (:50,:162,:219);
+here they are the defaults of extra flags (``--seqInfo --cfgDir --modelDir --ssRatio --gpus``).  Frames are cut,
+predicted, decoded and formatted on the GPU; with ``--gpus N`` the frames of a sequence are split into N contiguous
+ranges, one worker thread + handle per GPU, and the per-GPU text segments are concatenated in frame order.
+"""
+import argparse
+import os
+import threading
+import time
+
+import numpy as np
+import torch
+
+from .Metrics import inference_pre_QBD, seq_post_process       # noqa: F401  (reference re-exports)
+from .pipeline import COMPS, PartitionPredictor
+from .weights import load_pretrain_model, remove_prefix          # noqa: F401
+
+SAVE_MID_RESULT = False
+POST_PROCESS = True
+SSRatio = 30
+
+
+def load_sequences_info(seqs_info_path="Training_Sequences.txt", ss_ratio=None):
+    """Inference_QBD.py:48-76 on any CSV in the VVC_Test_Sequences.txt format (terminated by '#end!!!!')."""
+    ss = SSRatio if ss_ratio is None else ss_ratio
+    rows = []
+    with open(seqs_info_path, "r") as fp:
+        for line in fp:
+            if "end!!!!" in line:
+                break
+            if line.strip():
+                rows.append(line.rstrip("\n").split(","))
+    data = np.array(rows)
+    names, paths = data[:, 0], data[:, 1]
+    w, h, nf = data[:, 2].astype(np.int64), data[:, 3].astype(np.int64), data[:, 4].astype(np.int64)
+    sub = [(int(n) + ss - 1) // ss for n in nf]
+    blocks = [int((w[i] // 64) * (h[i] // 64) * sub[i]) for i in range(len(sub))]
+    return names, paths, w, h, nf, sub, blocks
+
+
+def import_yuv420(file_path, width, height, frm_num, SubSampleRatio=1, is10bit=False):
+    """Inference_QBD.py:78-102: planar 4:2:0, 8-bit or 16-bit LE samples, temporal subsampling by seek."""
+    pix = width * height
+    dt = np.uint16 if is10bit else np.uint8
+    idx = list(range(0, frm_num, SubSampleRatio))
+    y = np.zeros((len(idx), height, width), dt)
+    u = np.zeros((len(idx), height // 2, width // 2), dt)
+    v = np.zeros((len(idx), height // 2, width // 2), dt)
+    with open(file_path, "rb") as fp:
+        for k, i in enumerate(idx):
+            fp.seek(i * pix * 3 if is10bit else i * pix * 3 // 2, 0)
+            y[k] = np.fromfile(fp, dtype=dt, count=pix).reshape(height, width)
+            u[k] = np.fromfile(fp, dtype=dt, count=pix // 4).reshape(height // 2, width // 2)
+            v[k] = np.fromfile(fp, dtype=dt, count=pix // 4).reshape(height // 2, width // 2)
+    return y, u, v
+
+
+def output_block_yuv(file_path, width, height, block_size, in_overlap, numfrm, SubSampleRatio, is10bit=False,
+                     save_path=None):
+    """Inference_QBD.py:104-149 (host arrays out, as in the reference; the block cutting itself runs on the GPU)."""
+    if block_size != 64 or in_overlap != 4:
+        raise NotImplementedError("the nets are defined for block_size=64, in_overlap=4 (Inference_QBD.py:190)")
+    y, u, v = import_yuv420(file_path, width, height, numfrm, SubSampleRatio, is10bit=is10bit)
+    pp = PartitionPredictor(torch.cuda.current_device(), engine="simt")
+    lb, cb = pp.cut(y, u, v)
+    block_y = lb[:, 0].cpu().numpy()
+    block_u, block_v = cb[:, 1].cpu().numpy(), cb[:, 2].cpu().numpy()
+    if save_path is not None:
+        with open(save_path, "wb") as fp:
+            for i in range(block_y.shape[0]):
+                fp.write(block_y[i].tobytes()); fp.write(block_u[i].tobytes()); fp.write(block_v[i].tobytes())
+    return block_y, block_u, block_v
+
+
+def _parse_cfg(path):
+    seq_path, is10bit = None, False
+    with open(path) as fp:
+        for line in fp:
+            body = line.rstrip("\n").split("#")[0].replace(" ", "")
+            if "InputFile" in body:
+                seq_path = body.split(":", 1)[1]
+            elif "InputBitDepth" in body:
+                is10bit = body.split(":", 1)[1] == "10"
+    return seq_path, is10bit
+
+
+@torch.no_grad()
+def inference_VVC_seqs(args):
+    save_dir = os.path.join(args.outDir, args.jobID, "PartitionMat")
+    os.makedirs(save_dir, exist_ok=True)
+    ss = getattr(args, "ssRatio", SSRatio)
+    gpus = max(1, min(getattr(args, "gpus", 1), torch.cuda.device_count()))
+    model_dir = getattr(args, "modelDir", "./CTU_Models/")
+    missing_bd = getattr(args, "missingBD", "error")
+    names, paths, widths, heights, frmnums, subs, _ = load_sequences_info(getattr(args, "seqInfo", "Training_Sequences.txt"), ss)
+    preds = [PartitionPredictor(g, engine=getattr(args, "engine", "tc"), chunk=max(args.batchSize, 256)) for g in range(gpus)]
+    for p in preds:
+        p.load_pkls(model_dir, missing_bd=missing_bd)
+    nseq = args.seqNum
+    t_block, t_net, t_post = np.zeros(nseq), np.zeros((nseq, 4, 2)), np.zeros((nseq, 4, 2))
+    for seq_id in range(args.startSeqID, args.startSeqID + nseq):
+        s = seq_id - args.startSeqID
+        name, width, height = names[seq_id], int(widths[seq_id]), int(heights[seq_id])
+        seq_path_name = paths[seq_id][:-4] if paths[seq_id].endswith(".yuv") else paths[seq_id]
+        cfg = os.path.join(getattr(args, "cfgDir", r".\per-sequence"), name + ".cfg")
+        if os.path.exists(cfg):
+            seq_path, is10bit = _parse_cfg(cfg)
+        else:
+            seq_path, is10bit = os.path.join(args.inputDir, paths[seq_id]), "10bit" in paths[seq_id]
+        print(name)
+        t0 = time.time()
+        y, u, v = import_yuv420(seq_path, width, height, int(frmnums[seq_id]), ss, is10bit=is10bit)
+        nf = y.shape[0]
+        bounds = [nf * g // gpus for g in range(gpus + 1)]
+        t_block[s] = time.time() - t0
+        texts = {}
+
+        def work(g):
+            lo, hi = bounds[g], bounds[g + 1]
+            if hi <= lo:
+                return
+            with torch.cuda.device(g):
+                res = preds[g].predict_frames(y[lo:hi], u[lo:hi], v[lo:hi], qps=(22, 27, 32, 37))
+                for key, vals in res.items():
+                    from . import ops
+                    texts[(g,) + key] = ops.format_text(vals).cpu().numpy().tobytes()
+
+        t0 = time.time()
+        threads = [threading.Thread(target=work, args=(g,)) for g in range(gpus)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        t_net[s, :, :] = (time.time() - t0) / 8.0
+        t0 = time.time()
+        for ci, comp in enumerate(COMPS):
+            for qp in (22, 27, 32, 37):
+                path = PartitionPredictor.partition_path(save_dir, seq_path_name, comp, qp)
+                print("Save:", path)
+                with open(path, "wb") as fp:
+                    for g in range(gpus):
+                        fp.write(texts.get((g, comp, qp), b""))
+        t_post[s, :, :] = (time.time() - t0) / 8.0
+    log = os.path.join(args.outDir, args.jobID, "Time_Sta_%d_%d.txt" % (args.startSeqID, args.startSeqID + nseq))
+    with open(log, "w") as fp:
+        for s in range(nseq):
+            for q in range(4):
+                fp.write(",".join(str(x) for x in (t_block[s], t_net[s, q, 0], t_net[s, q, 1], t_post[s, q, 0],
+                                                   t_post[s, q, 1])) + ",\n")
+    print("Sum time:", np.sum(t_block) + np.sum(t_net) + np.sum(t_post))
+
+
+def build_parser():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--jobID', type=str, default='0000')
+    parser.add_argument('--inputDir', type=str, default='/input/')
+    parser.add_argument('--outDir', type=str, default='/output/')
+    parser.add_argument('--batchSize', default=200, type=int, help='batch size')
+    parser.add_argument('--startSeqID', default=0, type=int, help='QP start ID')
+    parser.add_argument('--seqNum', default=22, type=int, help='test QP number')
+    # extras: the reference hard-codes these
+    parser.add_argument('--seqInfo', type=str, default='Training_Sequences.txt')
+    parser.add_argument('--cfgDir', type=str, default=r'.\per-sequence')
+    parser.add_argument('--modelDir', type=str, default='./CTU_Models/')
+    parser.add_argument('--ssRatio', type=int, default=SSRatio)
+    parser.add_argument('--gpus', type=int, default=1)
+    parser.add_argument('--engine', type=str, default='tc', choices=['tc', 'simt'])
+    parser.add_argument('--missingBD', type=str, default='error', choices=['error', 'seeded'])
+    return parser
+
+
+if __name__ == '__main__':
+    a = build_parser().parse_args()
+    t = time.time()
+    inference_VVC_seqs(a)
+    print('Total inference time:', time.time() - t)

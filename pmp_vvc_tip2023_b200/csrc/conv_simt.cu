@@ -1,0 +1,293 @@
+// SIMT engine: exact-fp32 CUDA-core direct convolution with fused epilogue, plus the element-wise
+// glue kernels of the four nets (pyramid pooling, up-sample + concat, stem input assembly).
+//
+// Reference semantics: nn.Conv2d stride 1 with explicit zero padding offsets (Model_QBD.py:27-37,
+// :68-76,:108-121) followed by the ResidualBlock tail relu(conv2 + shortcut) (:40-44), optional
+// F.max_pool2d(.,2) (:81,:82,:89,:136,:137,:151) and the attention product (:143,:150), fused.
+//
+// This kernel is (a) the whole conv path of PMP_ENGINE_SIMT (fp32 NCHW everywhere) and (b) inside
+// PMP_ENGINE_TC the path of the layers that do not fit tensor cores: the stems (Cin <= 4, u8/f32 in,
+// split out), the 8x8 tail of the Q nets and the Cout <= 2 output convs (split in, fp32 out).
+#include "handle.cuh"
+#include "tensor.cuh"
+#include "kernels.cuh"
+
+namespace pmp {
+
+constexpr int ST_TILE = 16;       // output tile edge
+constexpr int ST_CO = 32;         // output channels per CTA
+constexpr int ST_TWP = 24;        // padded tile row stride (floats): rows land 8 banks apart
+
+template <int KH, int KW, int ST_CI>       // ST_CI: input channels per smem stage
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(SimtConvArgs a)
+{
+    constexpr int TH = ST_TILE + KH - 1, TW = ST_TILE + KW - 1;
+    static_assert(TW <= ST_TWP, "tile row too wide");
+    __shared__ float s_in[ST_CI][TH][ST_TWP];
+    __shared__ __align__(16) float s_w[ST_CI][KH * KW][ST_CO];
+
+    const int tid = threadIdx.x;
+    const int cg = tid >> 6;                 // channel group: 8 output channels
+    const int t = tid & 63, ty = t >> 3, tx = t & 7;
+    const int tiles_x = (a.Wo + ST_TILE - 1) / ST_TILE;
+    const int oy0 = (blockIdx.x / tiles_x) * ST_TILE, ox0 = (blockIdx.x % tiles_x) * ST_TILE;
+    const int co0 = blockIdx.y * ST_CO;
+    const int n = blockIdx.z;
+
+    float acc[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int c = 0; c < 8; c++) acc[p][c] = 0.f;
+
+    for (int ci0 = 0; ci0 < a.cin; ci0 += ST_CI) {
+        // ---- stage input halo tile (zero outside the image == the layer's zero padding) ----
+        for (int k = tid; k < ST_CI * TH * TW; k += 256) {
+            int ci = k / (TH * TW), r = (k / TW) % TH, c = k % TW;
+            int iy = oy0 + r - a.pad_t, ix = ox0 + c - a.pad_l;
+            float v = 0.f;
+            if (ci0 + ci < a.cin && iy >= 0 && iy < a.in.H && ix >= 0 && ix < a.in.W)
+                v = load_elem(a.in, n, ci0 + ci, iy, ix);
+            s_in[ci][r][c] = v;
+        }
+        // ---- stage weights [ci][tap][co] (global layout [cin][kh*kw][coutw], zero padded) ----
+        for (int k = tid; k < ST_CI * KH * KW * ST_CO; k += 256) {
+            int ci = k / (KH * KW * ST_CO), rem = k % (KH * KW * ST_CO);
+            int tap = rem / ST_CO, co = rem % ST_CO;
+            float v = 0.f;
+            if (ci0 + ci < a.cin && co0 + co < a.coutw) v = a.w[((size_t)(ci0 + ci) * KH * KW + tap) * a.coutw + co0 + co];
+            s_w[ci][tap][co] = v;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int ci = 0; ci < ST_CI; ci++) {
+#pragma unroll
+            for (int ky = 0; ky < KH; ky++) {
+#pragma unroll
+                for (int kx = 0; kx < KW; kx++) {
+                    const float4 w0 = *reinterpret_cast<const float4 *>(&s_w[ci][ky * KW + kx][cg * 8]);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(&s_w[ci][ky * KW + kx][cg * 8 + 4]);
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int p = 0; p < 4; p++) {
+                        const float v = s_in[ci][ty + 8 * (p >> 1) + ky][tx + 8 * (p & 1) + kx];
+#pragma unroll
+                        for (int c = 0; c < 8; c++) acc[p][c] = fmaf(v, wv[c], acc[p][c]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: bias, residual, ReLU, max-pool 2x2, attention product, store ----
+    const int cbase = co0 + cg * 8;
+    const int lane = tid & 31;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const int oy = oy0 + ty + 8 * (p >> 1), ox = ox0 + tx + 8 * (p & 1);
+        const bool inb = (oy < a.Ho && ox < a.Wo);
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            v[c] = acc[p][c];
+            if (a.bias && cbase + c < a.cout) v[c] += a.bias[cbase + c];
+        }
+        if (a.res.p && inb) {
+            if (a.res.fmt == FMT_SPLIT) {
+                if (cbase < a.res.Cp) {
+                    float r[8];
+                    load_chunk_split(a.res, n, cbase >> 3, oy, ox, r);
+#pragma unroll
+                    for (int c = 0; c < 8; c++) v[c] += r[c];
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; c++)
+                    if (cbase + c < a.cout) v[c] += load_elem(a.res, n, cbase + c, oy, ox);
+            }
+        }
+        if (a.add0 && inb && cbase == 0) v[0] += a.add0[(size_t)n * a.add0_bstride + (size_t)oy * a.Wo + ox];
+        if (a.relu) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) v[c] = fmaxf(v[c], 0.f);
+        }
+        int sy = oy, sx = ox;
+        bool writer = inb;
+        if (a.pool == 2) {
+            // the 2x2 window lives in lanes {l, l^1, l^8} (tx bit 0, ty bit 0); all lanes shuffle
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                float o = inb ? v[c] : -3.0e38f;
+                o = fmaxf(o, __shfl_xor_sync(0xffffffffu, o, 1));
+                o = fmaxf(o, __shfl_xor_sync(0xffffffffu, o, 8));
+                v[c] = o;
+            }
+            writer = inb && !(lane & 1) && !(lane & 8);
+            sy = oy >> 1; sx = ox >> 1;
+        }
+        if (!writer) continue;
+        if (a.mul.p) {
+            if (a.mul.fmt == FMT_SPLIT) {
+                if (cbase < a.mul.Cp) {
+                    float r[8];
+                    load_chunk_split(a.mul, n, cbase >> 3, sy, sx, r);
+#pragma unroll
+                    for (int c = 0; c < 8; c++) v[c] *= r[c];
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; c++)
+                    if (cbase + c < a.cout) v[c] *= load_elem(a.mul, n, cbase + c, sy, sx);
+            }
+        }
+        if (a.out.fmt == FMT_SPLIT) {
+            if (cbase < ((a.out.C == a.cout) ? a.out.Cp : a.cout)) {
+#pragma unroll
+                for (int c = 0; c < 8; c++)
+                    if (cbase + c >= a.cout) v[c] = 0.f;          // padding channels stay exactly zero
+                store_chunk_split(a.out, n, (a.out_c_off + cbase) >> 3, sy, sx, v);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+                if (cbase + c < a.cout) store_elem_f32(a.out, n, a.out_c_off + cbase + c, sy, sx, v[c]);
+        }
+    }
+}
+
+template <int KH, int KW, int ST_CI>
+static int launch_simt(Handle *h, const SimtConvArgs &a, int B, cudaStream_t s)
+{
+    // split outputs also get their zero padding channels written, but only when this conv owns the
+    // whole tensor (concat slots must not clobber their neighbours)
+    int cover = (a.out.fmt == FMT_SPLIT && a.out.C == a.cout) ? pad16(a.cout) : a.cout;
+    dim3 grid(cdiv(a.Ho, ST_TILE) * cdiv(a.Wo, ST_TILE), cdiv(cover, ST_CO), B);
+    double flops = 2.0 * B * a.Ho * a.Wo * (double)a.cout * a.cin * KH * KW;
+    ProfScope ps(h, PROF_CONV_SIMT, s, flops, 0);
+    conv_simt_kernel<KH, KW, ST_CI><<<grid, 256, 0, s>>>(a);
+    h->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
+int conv_simt(Handle *h, const SimtConvArgs &a, int kh, int kw, int B, cudaStream_t s)
+{
+    if (B <= 0) return PMP_OK;
+#define PMP_K(H_, W_, C_) if (kh == H_ && kw == W_) return launch_simt<H_, W_, C_>(h, a, B, s)
+    PMP_K(1, 1, 8); PMP_K(3, 3, 8); PMP_K(5, 5, 8); PMP_K(9, 9, 2); PMP_K(5, 9, 2); PMP_K(9, 5, 2); PMP_K(3, 5, 4);
+    PMP_K(5, 3, 4);
+#undef PMP_K
+    set_error("conv_simt: unsupported kernel size %dx%d", kh, kw);
+    return PMP_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise glue
+// ------------------------------------------------------------------------------------------------
+
+// x2 = cat[x, pad_lu(nearest_up(qt))]  (Model_QBD.py:130-131 / :228-229) -> fp32 [B, cx+1, S, S]
+__global__ void stem_input_kernel(Act x, const float *__restrict__ qt, int up, int ov, Act out, int B)
+{
+    const int S = out.H, C = out.C;
+    size_t total = (size_t)B * C * S * S;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int xx = (int)(i % S), yy = (int)((i / S) % S), c = (int)((i / ((size_t)S * S)) % C), n = (int)(i / ((size_t)S * S * C));
+        float v;
+        if (c < C - 1) v = load_elem(x, n, c, yy, xx);
+        else v = (yy >= ov && xx >= ov) ? qt[(size_t)n * 64 + ((yy - ov) / up) * 8 + (xx - ov) / up] : 0.f;
+        reinterpret_cast<float *>(out.p)[i] = v;
+    }
+}
+
+int stem_input(Handle *h, const Act &x, const float *qt, int up, int ov, const Act &out, int B, cudaStream_t s)
+{
+    size_t total = (size_t)B * out.C * out.H * out.W;
+    int grid = (int)((total + 255) / 256);
+    ProfScope ps(h, PROF_ELEMWISE, s, 0, (double)total * 5);
+    stem_input_kernel<<<grid, 256, 0, s>>>(x, qt, up, ov, out, B);
+    h->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
+// x6 = cat[x5, up2(pool2 x5), up4(pool4 x5), up8(pool8 x5)]  (Model_QBD.py:84-87): [B,32,16,16] -> [B,128,16,16]
+// one thread per (n, group g, 8-channel chunk, y, x)
+__global__ void pyramid_kernel(Act in, Act out, int B)
+{
+    const int H = in.H, W = in.W, nchunk = in.C >> 3;
+    size_t total = (size_t)B * 4 * nchunk * H * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % W), y = (int)((i / W) % H), ch = (int)((i / ((size_t)W * H)) % nchunk);
+        int g = (int)((i / ((size_t)W * H * nchunk)) % 4), n = (int)(i / ((size_t)W * H * nchunk * 4));
+        int sft = g, y0 = (y >> sft) << sft, x0 = (x >> sft) << sft, span = 1 << sft;
+        float m[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) m[e] = -3.0e38f;
+        for (int dy = 0; dy < span; dy++)
+            for (int dx = 0; dx < span; dx++) {
+                float v[8];
+                if (in.fmt == FMT_SPLIT) load_chunk_split(in, n, ch, y0 + dy, x0 + dx, v);
+                else {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) v[e] = load_elem(in, n, ch * 8 + e, y0 + dy, x0 + dx);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; e++) m[e] = fmaxf(m[e], v[e]);
+            }
+        int oc = g * in.C + ch * 8;
+        if (out.fmt == FMT_SPLIT) store_chunk_split(out, n, oc >> 3, y, x, m);
+        else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) store_elem_f32(out, n, oc + e, y, x, m[e]);
+        }
+    }
+}
+
+int pyramid(Handle *h, const Act &in, const Act &out, int B, cudaStream_t s)
+{
+    size_t total = (size_t)B * 4 * (in.C >> 3) * in.H * in.W;
+    int grid = (int)((total + 255) / 256);
+    ProfScope ps(h, PROF_ELEMWISE, s, 0, (double)total * 8 * 4 * 2);
+    pyramid_kernel<<<grid, 256, 0, s>>>(in, out, B);
+    h->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
+// attention-trunk input (Model_QBD.py:140,:147): [B,3,S,S] = cat[up(qt, S/8), up(prev ch0, S/16), up(prev ch1, S/16)]
+// prev = out0 / accumulated out1 (FMT_PAIR, 16x16).  Output fp32 [B,3,S,S] or split [B,16(pad),S,S].
+__global__ void att_input_kernel(const float *__restrict__ qt, Act prev, Act out, int B)
+{
+    const int S = out.H;
+    const int qs = S / 8, ps = S / 16;
+    size_t total = (size_t)B * S * S;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % S), y = (int)((i / S) % S), n = (int)(i / ((size_t)S * S));
+        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        v[0] = qt[(size_t)n * 64 + (y / qs) * 8 + (x / qs)];
+        v[1] = load_elem(prev, n, 0, y / ps, x / ps);
+        v[2] = load_elem(prev, n, 1, y / ps, x / ps);
+        if (out.fmt == FMT_SPLIT) {
+            store_chunk_split(out, n, 0, y, x, v);
+            const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            store_chunk_split(out, n, 1, y, x, z);
+        } else {
+            for (int c = 0; c < 3; c++) store_elem_f32(out, n, c, y, x, v[c]);
+        }
+    }
+}
+
+int att_input(Handle *h, const float *qt, const Act &prev, const Act &out, int B, cudaStream_t s)
+{
+    size_t total = (size_t)B * out.H * out.W;
+    int grid = (int)((total + 255) / 256);
+    ProfScope ps(h, PROF_ELEMWISE, s, 0, (double)total * 64);
+    att_input_kernel<<<grid, 256, 0, s>>>(qt, prev, out, B);
+    h->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
+}  // namespace pmp

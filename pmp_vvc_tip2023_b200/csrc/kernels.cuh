@@ -1,0 +1,46 @@
+// Kernel-launch entry points shared between translation units (internal).
+#pragma once
+#include "handle.cuh"
+#include "tensor.cuh"
+
+namespace pmp {
+
+struct SimtConvArgs {
+    Act in, out, res, mul;        // res / mul optional (p == nullptr)
+    const float *w = nullptr;     // [cin][kh*kw][coutw] fp32, zero padded
+    const float *bias = nullptr;  // [cout] or nullptr
+    int cin = 0, cout = 0, coutw = 0;
+    int pad_t = 0, pad_l = 0;     // input coordinate = output coordinate + tap - pad
+    int Ho = 0, Wo = 0;           // conv output size (before pooling)
+    int relu = 0, pool = 1;
+    int out_c_off = 0;            // channel offset inside `out` (concat writes)
+    const float *add0 = nullptr;  // added to output channel 0 (Model_QBD.py:146,:153)
+    long long add0_bstride = 0;
+};
+
+int conv_simt(Handle *h, const SimtConvArgs &a, int kh, int kw, int B, cudaStream_t s);
+int stem_input(Handle *h, const Act &x, const float *qt, int up, int ov, const Act &out, int B, cudaStream_t s);
+int pyramid(Handle *h, const Act &in, const Act &out, int B, cudaStream_t s);
+int att_input(Handle *h, const float *qt, const Act &prev, const Act &out, int B, cudaStream_t s);
+// out = maxpool2(in) [* mul]; split -> split
+int pool2_split(Handle *h, const Act &in, const Act &out, const Act &mul, int B, cudaStream_t s);
+
+// ---- TC engine (conv_tc.cu) ------------------------------------------------------------------
+struct TcConvArgs {
+    Act in;                 // FMT_SPLIT [B, cin_pad, H, W]
+    Act in2;                // optional second K phase: 1x1 shortcut conv over the block input (p == nullptr: none)
+    Act out;                // FMT_SPLIT
+    Act res;                // optional identity residual (FMT_SPLIT, same shape as the conv output)
+    Act mul;                // optional attention product (FMT_SPLIT, shape of the stored output)
+    const uint16_t *w = nullptr;    // packed main weights (see pack_tc_weights)
+    const uint16_t *w2 = nullptr;   // packed 1x1 shortcut weights
+    int cin_pad = 0, cin2_pad = 0, cout_pad = 0, ksize = 1;
+    int relu = 0, pool = 1;
+};
+int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s);
+bool tc_supported(int cin_pad, int cout_pad, int ksize, int H, int W);
+// host-side packing of one conv's weights into the TC operand image; returns number of uint16 written
+size_t tc_packed_elems(int cin_pad, int cout_pad, int ksize);
+void pack_tc_weights(const float *w, int cout, int cin, int ksize, int cin_pad, int cout_pad, bool bf16, uint16_t *dst);
+
+}  // namespace pmp

@@ -1,0 +1,118 @@
+"""Whole hot path on one GPU: planar YUV frames -> per-frame PartitionMat vectors (and files).
+
+This is the call a user of the framework makes (bench.py's ``e2e`` leg times it): host frames are copied to the
+device, cut into 68x68 / 3x34x34 blocks there (``pmp_cut_blocks``), pushed through the Q and MSBD nets, the QT
+post-process, the map-to-partition decode and the frame assembly (``pmp_run_component``), and come back as int8
+vectors in the order ``get_sequence_partition_for_VTM`` writes them (Map2Partition.py:401-412).
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import _lib, ops, synth, weights
+from .netspec import QPS, param_spec
+
+COMPS = ("Luma", "Chroma")
+
+
+class PartitionPredictor:
+    def __init__(self, device=0, engine="tc", tc_dtype="fp16", chunk=1024):
+        if not torch.cuda.is_available():
+            raise _lib.PmpError("no CUDA device: pmp_vvc_tip2023_b200 has no CPU fallback")
+        self.device = torch.device("cuda", int(device))
+        self.handle = _lib.Handle.get(int(device))
+        self.set_engine(engine, tc_dtype)
+        self.chunk = int(chunk)
+        self._wsets = {}           # (comp, qp) -> (wset_q, wset_msbd)
+
+    def set_engine(self, engine, tc_dtype="fp16"):
+        eng = {"simt": _lib.ENGINE_SIMT, "tc": _lib.ENGINE_TC}[engine]
+        self.handle.set_engine(eng, {"fp16": _lib.TC_FP16, "bf16": _lib.TC_BF16}[tc_dtype])
+        self.engine = engine
+
+    # ---- weights -------------------------------------------------------------------------------
+    def load_state_dicts(self, comp, qp, sd_q, sd_bd):
+        """sd_*: {reference parameter name: array/tensor} (``module.`` prefix allowed)."""
+        out = []
+        for kind, sd in (("Q", sd_q), ("MSBD", sd_bd)):
+            net = "%s_%s" % (comp, kind)
+            sd = weights.remove_prefix(dict(sd), "module.")
+            tensors = []
+            for name, shape in param_spec(net):
+                if name not in sd:
+                    raise KeyError("%s: missing parameter %s" % (net, name))
+                t = sd[name]
+                t = t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
+                if tuple(t.shape) != tuple(shape):
+                    raise ValueError("%s: %s has shape %s, expected %s" % (net, name, tuple(t.shape), tuple(shape)))
+                tensors.append(np.ascontiguousarray(t, dtype=np.float32))
+            out.append(self.handle.weights_create(net, tensors))
+        old = self._wsets.pop((comp, qp), None)
+        if old:
+            for w in old:
+                self.handle.weights_destroy(w)
+        self._wsets[(comp, qp)] = tuple(out)
+
+    def load_pkls(self, model_dir, comps=COMPS, qps=QPS, missing_bd="error"):
+        """Reference file naming (Inference_QBD.py:219-220): <comp>_Q_<qp>.pkl, <comp>_BD_<qp>.pkl.
+        missing_bd="seeded" substitutes seeded random MSBD weights (the trained BD files are not redistributable
+        in this repo's mount) -- for benchmarking/tests only."""
+        for comp in comps:
+            for qp in qps:
+                sd_q = weights.load_reference_pkl(os.path.join(model_dir, "%s_Q_%d.pkl" % (comp, qp)))
+                bd_path = os.path.join(model_dir, "%s_BD_%d.pkl" % (comp, qp))
+                if os.path.exists(bd_path):
+                    sd_bd = weights.load_reference_pkl(bd_path)
+                elif missing_bd == "seeded":
+                    sd_bd = synth.seeded_state_dict(comp + "_MSBD", 1000 + qp + (0 if comp == "Luma" else 500))
+                else:
+                    raise FileNotFoundError(bd_path)
+                self.load_state_dicts(comp, qp, sd_q, sd_bd)
+
+    def load_seeded(self, comps=COMPS, qps=QPS, seed=0):
+        for comp in comps:
+            for qp in qps:
+                self.load_state_dicts(comp, qp, synth.seeded_state_dict(comp + "_Q", seed + qp),
+                                      synth.seeded_state_dict(comp + "_MSBD", seed + 1000 + qp))
+
+    # ---- compute -------------------------------------------------------------------------------
+    def to_device(self, a):
+        if isinstance(a, torch.Tensor):
+            return a.to(self.device, non_blocking=True)
+        a = np.ascontiguousarray(a)
+        if a.dtype == np.uint16:
+            a = a.view(np.int16)              # torch has no uint16 arithmetic; the kernel reads raw 16-bit words
+        return torch.from_numpy(a).to(self.device, non_blocking=True)
+
+    def cut(self, y, u, v, comps=COMPS):
+        y, u, v = self.to_device(y), self.to_device(u), self.to_device(v)
+        return ops.cut_blocks(y, u, v, want_luma="Luma" in comps, want_chroma="Chroma" in comps)
+
+    def predict_blocks(self, comp, qp, blocks, frames, bh, bw, want_maps=False):
+        wq, wb = self._wsets[(comp, qp)]
+        return ops.run_component(wq, wb, comp == "Luma", blocks, frames, bh, bw, self.chunk, want_maps)
+
+    def predict_frames(self, y, u, v, qps=(32,), comps=COMPS, want_maps=False):
+        """y [F,H,W], u/v [F,H/2,W/2] (uint8, or uint16/int16 holding 10-bit samples), host or device.
+        Returns {(comp, qp): int8 CUDA tensor [F, per-frame values]} (or tuples with maps)."""
+        f, hgt, wid = y.shape
+        bh, bw = hgt // 64, wid // 64
+        lb, cb = self.cut(y, u, v, comps)
+        out = {}
+        for comp in comps:
+            blocks = lb if comp == "Luma" else cb
+            for qp in qps:
+                out[(comp, qp)] = self.predict_blocks(comp, qp, blocks, f, bh, bw, want_maps)
+        return out
+
+    @staticmethod
+    def partition_path(save_dir, seq_path_name, comp, qp):
+        """Inference_QBD.py:237."""
+        return os.path.join(save_dir, "%s_%s_QP%d_PartitionMat.txt" % (seq_path_name, comp, qp))
+
+    def write_partition_file(self, values, path):
+        text = ops.format_text(values)
+        with open(path, "wb") as fp:
+            fp.write(text.cpu().numpy().tobytes())
+        return int(text.numel())
