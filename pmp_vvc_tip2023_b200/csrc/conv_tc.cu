@@ -1,11 +1,621 @@
-// placeholder until the tcgen05 engine lands (same translation unit name)
+// TC engine: stride-1 "same" convolution (1x1 / 3x3 / 5x5) as an implicit GEMM on the 5th-gen tensor cores.
+//
+//   D[pixels, cout] += A[pixels, cin] * W[cin, cout]   per filter tap, fp32 accumulation in TMEM.
+//
+// Split precision (single-pass 16-bit operands miss the 1e-2 parity bar): activations and
+// weights are stored as hi + lo 16-bit pairs and three products are accumulated,
+//   a_hi*w_hi + a_hi*w_lo + a_lo*w_hi        (error ~ a_lo*w_lo ~ 2^-22 relative with fp16),
+// as two tcgen05.mma per K=16 step: (a_hi) x [w_hi | w_lo] with N = 2*Cout into columns [0, 2*Cout) of the M-tile's
+// accumulator, then (a_lo) x [w_hi] with N = Cout into columns [0, Cout).  The epilogue adds the two column halves.
+//
+// Tiling ("halo-resident linear tile"): a CTA owns up to 4 M-tiles of 128 consecutive positions of ONE image, counted on
+// the zero-padded pitch P = W + k - 1.  One TMA box per 16-channel group (8 x P x rows x 4 planes) brings the halo tile
+// of the FMT_SPLIT activation (tensor.cuh) into shared memory exactly in the no-swizzle K-major UMMA layout, TMA's
+// out-of-bounds zero fill providing the convolution's zero padding.  Because the tile is linear on pitch P, the A
+// operand of filter tap (ky,kx) is the same descriptor advanced by (ky*P + kx)*16 bytes; positions that fall into the
+// P-W pad columns compute garbage that the epilogue drops (W/P = 94..97 % efficiency).  Weights stream through a
+// shared-memory ring, one (tap, channel-group) slab [2][N][8] per stage via cp.async.bulk, pre-packed on the host.
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 = epilogue (TMEM -> registers ->
+// residual add / ReLU / attention product -> hi/lo split -> coalesced 16-byte stores); warp 2 owns the TMEM allocation.
 #include "handle.cuh"
 #include "kernels.cuh"
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+
 namespace pmp {
-bool tc_supported(int, int, int, int, int) { return false; }
-size_t tc_packed_elems(int, int, int) { return 0; }
-void pack_tc_weights(const float *, int, int, int, int, int, bool, uint16_t *) {}
-int conv_tc(Handle *, const TcConvArgs &, int, cudaStream_t) { set_error("TC engine not built"); return PMP_ERR_UNSUPPORTED; }
-int pool2_split(Handle *, const Act &, const Act &, const Act &, int, cudaStream_t) { set_error("TC engine not built"); return PMP_ERR_UNSUPPORTED; }
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 12;
+constexpr int TC_MAX_GROUPS = 8;
+constexpr uint32_t TC_SMEM_HEADER = 1024;
+constexpr uint32_t TC_SMEM_MAX = 232448;          // 227 KB dynamic shared memory per CTA
+
+struct TcGeom {
+    int P, MT, total_mt, tiles, Rbox, groups, N1, coutp, nstages;
+    uint32_t plane_bytes, group_bytes, act_bytes, stage_bytes, smem_bytes, tmem_cols;
+};
+
+static bool tc_geometry(int cin_pad, int cout_pad, int k, int H, int W, TcGeom &g)
+{
+    if (!(k == 1 || k == 3 || k == 5)) return false;
+    if (cin_pad % 16 || cout_pad % 16 || cin_pad < 16 || cout_pad < 16 || cout_pad > 64) return false;
+    if (H < 16 || W < 16 || (W & 1)) return false;
+    g.groups = cin_pad / 16;
+    if (g.groups > TC_MAX_GROUPS) return false;
+    g.coutp = cout_pad;
+    g.N1 = 2 * cout_pad;
+    g.P = W + k - 1;
+    g.total_mt = (H * g.P + 127) / 128;
+    g.stage_bytes = 32u * g.N1;
+    for (int mt = (g.total_mt < 4 ? g.total_mt : 4); mt >= 1; mt--) {
+        int maxidx = g.P - 1 + mt * 128 - 1 + (k - 1) * (g.P + 1);
+        int rbox = maxidx / g.P + 1;
+        if (rbox > 256) continue;
+        uint32_t plane = (uint32_t)rbox * g.P * 16;
+        uint32_t act = plane * 4 * g.groups;
+        if (TC_SMEM_HEADER + act + 4 * g.stage_bytes > TC_SMEM_MAX) continue;
+        int ns = (int)((TC_SMEM_MAX - TC_SMEM_HEADER - act) / g.stage_bytes);
+        if (ns > TC_MAX_STAGES) ns = TC_MAX_STAGES;
+        g.MT = mt; g.Rbox = rbox; g.plane_bytes = plane; g.group_bytes = plane * 4; g.act_bytes = act;
+        g.nstages = ns;
+        g.smem_bytes = TC_SMEM_HEADER + act + ns * g.stage_bytes;
+        g.tiles = (g.total_mt + mt - 1) / mt;
+        uint32_t cols = (uint32_t)mt * g.N1, pc = 32;
+        while (pc < cols) pc <<= 1;
+        g.tmem_cols = pc;
+        return pc <= 512;
+    }
+    return false;
 }
-extern "C" int pmp_selftest_conv(pmp_handle *, int, int, int, int, int, int, double *, double *, double *, double *) { return PMP_ERR_UNSUPPORTED; }
+
+bool tc_supported(int cin_pad, int cout_pad, int ksize, int H, int W)
+{
+    TcGeom g;
+    return tc_geometry(cin_pad, cout_pad, ksize, H, W, g);
+}
+
+size_t tc_packed_elems(int cin_pad, int cout_pad, int ksize)
+{
+    return (size_t)ksize * ksize * (cin_pad / 16) * 2 * (2 * cout_pad) * 8;
+}
+
+static inline void host_split(float w, bool bf16, uint16_t &hi, uint16_t &lo)
+{
+    if (bf16) {
+        __nv_bfloat16 h = __float2bfloat16_rn(w);
+        __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+        hi = *reinterpret_cast<uint16_t *>(&h); lo = *reinterpret_cast<uint16_t *>(&l);
+    } else {
+        __half h = __float2half_rn(w);
+        __half l = __float2half_rn(w - __half2float(h));
+        hi = *reinterpret_cast<uint16_t *>(&h); lo = *reinterpret_cast<uint16_t *>(&l);
+    }
+}
+
+// [tap][group][k8 (2)][n (2*cout_pad: hi couts then lo couts)][8 cin] 16-bit; w is the reference's [cout][cin][k][k] fp32
+void pack_tc_weights(const float *w, int cout, int cin, int ksize, int cin_pad, int cout_pad, bool bf16, uint16_t *dst)
+{
+    const int groups = cin_pad / 16, N1 = 2 * cout_pad, taps = ksize * ksize;
+    for (int t = 0; t < taps; t++)
+        for (int g = 0; g < groups; g++)
+            for (int k8 = 0; k8 < 2; k8++)
+                for (int n = 0; n < cout_pad; n++)
+                    for (int e = 0; e < 8; e++) {
+                        const int c = g * 16 + k8 * 8 + e;
+                        uint16_t hi = 0, lo = 0;
+                        if (n < cout && c < cin) host_split(w[((size_t)n * cin + c) * taps + t], bf16, hi, lo);
+                        const size_t base = (((size_t)t * groups + g) * 2 + k8) * N1 * 8;
+                        dst[base + (size_t)n * 8 + e] = hi;
+                        dst[base + (size_t)(cout_pad + n) * 8 + e] = lo;
+                    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4)
+{
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// element (row, k) lives at start + (row/8)*SBO + (row%8)*16 + (k/8)*LBO + (k%8)*2
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+
+struct TcParams {
+    const uint16_t *w;
+    Act out, res, mul;
+    int H, W, P, k, pad, groups, MT, total_mt, N1, coutp, nstages;
+    uint32_t plane_bytes, group_bytes, stage_bytes, tmem_cols, idesc1, idesc2;
+    int relu, variant;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+    // barrier slots: [0,8) act_full, [8,8+12) w_full, [24,24+12) w_empty, [40] acc_full
+    const uint32_t bar_act = smem_u32(bars), bar_wfull = smem_u32(bars + 8), bar_wempty = smem_u32(bars + 24),
+                   bar_acc = smem_u32(bars + 40);
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 512);
+    uint8_t *act = smem + TC_SMEM_HEADER;
+    uint8_t *ring = act + (size_t)p.groups * p.group_bytes;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.y;
+    const int mt0 = blockIdx.x * p.MT;
+    const int mt_count = (p.total_mt - mt0 < p.MT) ? (p.total_mt - mt0) : p.MT;
+    const int q0 = mt0 * 128;
+    const int row0 = q0 / p.P, qoff = q0 - row0 * p.P;
+    const int nst_total = p.k * p.k * p.groups;
+
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < p.groups; g++) mbar_init(bar_act + 8 * g, 1);
+        for (int s = 0; s < p.nstages; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + 512)),
+                     "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== producer: activation halo tile (one box per 16-channel group), then the weight ring =====
+            for (int g = 0; g < p.groups; g++) {
+                mbar_expect_tx(bar_act + 8 * g, p.group_bytes);
+                tma_load_5d(smem_u32(act + (size_t)g * p.group_bytes), &tmap, bar_act + 8 * g, 0, -p.pad, row0 - p.pad,
+                            g * 4, n);
+            }
+            const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(p.w);
+            for (int it = 0; it < nst_total; it++) {
+                const int s = it % p.nstages;
+                const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+                mbar_wait(bar_wempty + 8 * s, ph ^ 1u);
+                mbar_expect_tx(bar_wfull + 8 * s, p.stage_bytes);
+                bulk_g2s(smem_u32(ring + (size_t)s * p.stage_bytes), wsrc + (size_t)it * p.stage_bytes, p.stage_bytes,
+                         bar_wfull + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t act_s = smem_u32(act), ring_s = smem_u32(ring);
+            const uint32_t lboA = (p.variant & 1) ? 128u : p.plane_bytes, sboA = (p.variant & 1) ? p.plane_bytes : 128u;
+            const uint32_t lboB = (p.variant & 1) ? 128u : (uint32_t)p.N1 * 16u, sboB = (p.variant & 1) ? (uint32_t)p.N1 * 16u : 128u;
+            for (int it = 0; it < nst_total; it++) {
+                const int s = it % p.nstages;
+                const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+                const int tap = it / p.groups, g = it - tap * p.groups;
+                const int ky = tap / p.k, kx = tap - ky * p.k;
+                if (tap == 0) mbar_wait(bar_act + 8 * g, 0);
+                mbar_wait(bar_wfull + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t a0 = act_s + (uint32_t)g * p.group_bytes + (uint32_t)(qoff + ky * p.P + kx) * 16u;
+                const uint64_t bdesc = umma_desc(ring_s + (uint32_t)s * p.stage_bytes, lboB, sboB);
+                for (int mt = 0; mt < mt_count; mt++) {
+                    const uint32_t a_hi = a0 + (uint32_t)mt * 2048u;
+                    const uint32_t d = tmem_base + (uint32_t)(mt * p.N1);
+                    umma_f16(d, umma_desc(a_hi, lboA, sboA), bdesc, p.idesc1, it > 0 ? 1u : 0u);
+                    umma_f16(d, umma_desc(a_hi + 2u * p.plane_bytes, lboA, sboA), bdesc, p.idesc2, 1u);
+                }
+                umma_commit(bar_wempty + 8 * s);       // frees the weight slot once these MMAs have read it
+            }
+            umma_commit(bar_acc);                       // accumulators complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;
+        const int nchunk = p.coutp >> 3;
+        for (int mt = 0; mt < mt_count; mt++) {
+            const int pos = q0 + mt * 128 + quarter * 32 + lane;
+            const int r = pos / p.P, c = pos - r * p.P;
+            const bool valid = (c < p.W) && (r < p.H);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * p.N1);
+            for (int j = 0; j < nchunk; j++) {
+                uint32_t hi[8], lo[8];
+                tmem_ld8(taddr + 8 * j, hi);
+                tmem_ld8(taddr + p.coutp + 8 * j, lo);
+                tmem_wait_ld();
+                if (!valid) continue;
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) v[e] = __uint_as_float(hi[e]) + __uint_as_float(lo[e]);
+                if (p.res.p) {
+                    float rv[8];
+                    load_chunk_split(p.res, n, j, r, c, rv);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) v[e] += rv[e];
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) v[e] = fmaxf(v[e], 0.f);
+                }
+                if (p.mul.p) {
+                    float mv[8];
+                    load_chunk_split(p.mul, n, j, r, c, mv);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) v[e] *= mv[e];
+                }
+                store_chunk_split(p.out, n, j, r, c, v);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encoder(Handle *h, EncodeTiledFn *fn)
+{
+    if (!h->encode_tiled) {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        PMP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !f) {
+            set_error("cuTensorMapEncodeTiled is not available from the driver");
+            return PMP_ERR_UNSUPPORTED;
+        }
+        h->encode_tiled = f;
+    }
+    *fn = reinterpret_cast<EncodeTiledFn>(h->encode_tiled);
+    return PMP_OK;
+}
+
+static int g_tc_variant = 0;       // descriptor variant for the self test (0 = as designed)
+
+int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
+{
+    if (B <= 0) return PMP_OK;
+    TcGeom g;
+    const int H = a.in.H, W = a.in.W;
+    if (a.in.fmt != FMT_SPLIT || a.out.fmt != FMT_SPLIT || !tc_geometry(a.cin_pad, a.cout_pad, a.ksize, H, W, g) ||
+        a.in.Cp != a.cin_pad || a.out.Cp != a.cout_pad || a.pool != 1 || a.in2.p) {
+        set_error("conv_tc: unsupported configuration cin %d cout %d k %d %dx%d", a.cin_pad, a.cout_pad, a.ksize, H, W);
+        return PMP_ERR_UNSUPPORTED;
+    }
+    EncodeTiledFn enc = nullptr;
+    int rc = get_encoder(h, &enc);
+    if (rc) return rc;
+    CUtensorMap tmap;
+    const cuuint64_t planes = (cuuint64_t)a.cin_pad / 4;
+    cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, planes, (cuuint64_t)B};
+    cuuint64_t gstr[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, planes * H * W * 16};
+    cuuint32_t box[5] = {8, (cuuint32_t)g.P, (cuuint32_t)g.Rbox, 4, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, a.in.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for W %d H %d planes %d B %d box %d x %d", (int)cr, W, H, (int)planes, B,
+                  g.P, g.Rbox);
+        return PMP_ERR_CUDA;
+    }
+    TcParams p;
+    p.w = a.w; p.out = a.out; p.res = a.res; p.mul = a.mul;
+    p.H = H; p.W = W; p.P = g.P; p.k = a.ksize; p.pad = a.ksize / 2; p.groups = g.groups; p.MT = g.MT;
+    p.total_mt = g.total_mt; p.N1 = g.N1; p.coutp = g.coutp; p.nstages = g.nstages;
+    p.plane_bytes = g.plane_bytes; p.group_bytes = g.group_bytes; p.stage_bytes = g.stage_bytes; p.tmem_cols = g.tmem_cols;
+    const uint32_t fmt = a.in.bf16 ? 1u : 0u;
+    const uint32_t idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 4) << 24);
+    p.idesc1 = idesc_base | ((uint32_t)(g.N1 >> 3) << 17);
+    p.idesc2 = idesc_base | ((uint32_t)(g.coutp >> 3) << 17);
+    p.relu = a.relu; p.variant = g_tc_variant;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PMP_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
+        attr_set = true;
+    }
+    dim3 grid(g.tiles, B);
+    const double flops = 2.0 * B * H * W * (double)a.out.C * a.in.C * a.ksize * a.ksize;
+    ProfScope ps(h, PROF_CONV_TC, s, flops, 0);
+    conv_tc_kernel<<<grid, TC_THREADS, g.smem_bytes, s>>>(tmap, p);
+    h->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// max-pool 2x2 (+ attention product) on split tensors; format conversion helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void pool2_split_kernel(Act in, Act out, Act mul, int B)
+{
+    const int Ho = out.H, Wo = out.W, nch = out.Cp >> 3;
+    size_t total = (size_t)B * nch * Ho * Wo;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % Wo), y = (int)((i / Wo) % Ho), ch = (int)((i / ((size_t)Wo * Ho)) % nch);
+        int n = (int)(i / ((size_t)Wo * Ho * nch));
+        float m[8], v[8];
+        load_chunk_split(in, n, ch, 2 * y, 2 * x, m);
+        load_chunk_split(in, n, ch, 2 * y, 2 * x + 1, v);
+#pragma unroll
+        for (int e = 0; e < 8; e++) m[e] = fmaxf(m[e], v[e]);
+        load_chunk_split(in, n, ch, 2 * y + 1, 2 * x, v);
+#pragma unroll
+        for (int e = 0; e < 8; e++) m[e] = fmaxf(m[e], v[e]);
+        load_chunk_split(in, n, ch, 2 * y + 1, 2 * x + 1, v);
+#pragma unroll
+        for (int e = 0; e < 8; e++) m[e] = fmaxf(m[e], v[e]);
+        if (mul.p) {
+            load_chunk_split(mul, n, ch, y, x, v);
+#pragma unroll
+            for (int e = 0; e < 8; e++) m[e] *= v[e];
+        }
+        store_chunk_split(out, n, ch, y, x, m);
+    }
+}
+
+int pool2_split(Handle *h, const Act &in, const Act &out, const Act &mul, int B, cudaStream_t s)
+{
+    size_t total = (size_t)B * (out.Cp >> 3) * out.H * out.W;
+    if (!total) return PMP_OK;
+    int grid = (int)((total + 255) / 256);
+    ProfScope ps(h, PROF_ELEMWISE, s, 0, (double)total * 32 * 5);
+    pool2_split_kernel<<<grid, 256, 0, s>>>(in, out, mul, B);
+    h->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
+__global__ void f32_to_split_kernel(const float *__restrict__ src, Act dst, int B)
+{
+    const int nch = dst.Cp >> 3;
+    size_t total = (size_t)B * nch * dst.H * dst.W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % dst.W), y = (int)((i / dst.W) % dst.H), ch = (int)((i / ((size_t)dst.W * dst.H)) % nch);
+        int n = (int)(i / ((size_t)dst.W * dst.H * nch));
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            int c = ch * 8 + e;
+            v[e] = c < dst.C ? src[(((size_t)n * dst.C + c) * dst.H + y) * dst.W + x] : 0.f;
+        }
+        store_chunk_split(dst, n, ch, y, x, v);
+    }
+}
+
+__global__ void split_to_f32_kernel(Act src, float *__restrict__ dst, int B)
+{
+    size_t total = (size_t)B * src.C * src.H * src.W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % src.W), y = (int)((i / src.W) % src.H), c = (int)((i / ((size_t)src.W * src.H)) % src.C);
+        int n = (int)(i / ((size_t)src.W * src.H * src.C));
+        dst[i] = load_elem(src, n, c, y, x);
+    }
+}
+
+}  // namespace pmp
+
+// ------------------------------------------------------------------------------------------------
+// self test: TC conv against the exact fp32 SIMT conv on the same split-precision inputs
+// ------------------------------------------------------------------------------------------------
+using namespace pmp;
+
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { return cudaMalloc(&p, bytes) == cudaSuccess ? 0 : -1; }
+};
+float lcg(uint32_t &s)
+{
+    s = s * 1664525u + 1013904223u;
+    return ((s >> 8) & 0xFFFF) / 32768.0f - 1.0f;
+}
+}  // namespace
+
+struct pmp_handle : public pmp::Handle {};
+
+// flags: bit0 relu, bit1 identity residual, bit2 attention product, bit3 bf16 operands, bits 8..15 descriptor variant,
+// bit 16: verbose mismatch report on stderr
+extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, int hw, int batch, int flags, double *max_err,
+                                 double *ref_absmax, double *ms_tc, double *ms_simt)
+{
+    if (!h) return PMP_ERR_ARG;
+    PMP_CUDA(cudaSetDevice(h->device));
+    const int B = batch, H = hw, W = hw;
+    const bool bf = (flags & 8) != 0;
+    const int cinp = pad16(cin), coutp = pad16(cout);
+    if (!tc_supported(cinp, coutp, ksize, H, W)) {
+        set_error("selftest: configuration not supported by the TC engine");
+        return PMP_ERR_UNSUPPORTED;
+    }
+    uint32_t seed = 12345u + cin * 7 + cout * 13 + ksize * 31 + hw;
+    const size_t n_in = (size_t)B * cin * H * W, n_out = (size_t)B * cout * H * W, n_w = (size_t)cout * cin * ksize * ksize;
+    std::vector<float> hin(n_in), hw_(n_w), hres(n_out), hmul(n_out);
+    for (auto &v : hin) v = 40.f * fabsf(lcg(seed)) * (lcg(seed) > -0.3f ? 1.f : 0.f);     // relu-like activations
+    const float wb = sqrtf(3.0f / (cin * ksize * ksize));
+    for (auto &v : hw_) v = wb * lcg(seed);
+    for (auto &v : hres) v = 10.f * lcg(seed);
+    for (auto &v : hmul) v = 1.5f * lcg(seed);
+
+    DevBuf d_in32, d_res32, d_mul32, d_in, d_res, d_mul, d_out, d_out32, d_ref32, d_wsimt, d_wtc;
+    const size_t sp_in = act_bytes(FMT_SPLIT, B, cin, H, W), sp_out = act_bytes(FMT_SPLIT, B, cout, H, W);
+    if (d_in32.alloc(n_in * 4) || d_res32.alloc(n_out * 4) || d_mul32.alloc(n_out * 4) || d_in.alloc(sp_in) ||
+        d_res.alloc(sp_out) || d_mul.alloc(sp_out) || d_out.alloc(sp_out) || d_out32.alloc(n_out * 4) ||
+        d_ref32.alloc(n_out * 4)) {
+        set_error("selftest: cudaMalloc failed");
+        return PMP_ERR_CUDA;
+    }
+    PMP_CUDA(cudaMemcpy(d_in32.p, hin.data(), n_in * 4, cudaMemcpyHostToDevice));
+    PMP_CUDA(cudaMemcpy(d_res32.p, hres.data(), n_out * 4, cudaMemcpyHostToDevice));
+    PMP_CUDA(cudaMemcpy(d_mul32.p, hmul.data(), n_out * 4, cudaMemcpyHostToDevice));
+    // weights: SIMT layout + TC packing
+    const int coutw = (cout + 3) & ~3, taps = ksize * ksize;
+    std::vector<float> ps((size_t)cin * taps * coutw, 0.f);
+    for (int o = 0; o < cout; o++)
+        for (int c = 0; c < cin; c++)
+            for (int t = 0; t < taps; t++) ps[((size_t)c * taps + t) * coutw + o] = hw_[((size_t)o * cin + c) * taps + t];
+    std::vector<uint16_t> pk(tc_packed_elems(cinp, coutp, ksize));
+    pack_tc_weights(hw_.data(), cout, cin, ksize, cinp, coutp, bf, pk.data());
+    if (d_wsimt.alloc(ps.size() * 4) || d_wtc.alloc(pk.size() * 2)) return PMP_ERR_CUDA;
+    PMP_CUDA(cudaMemcpy(d_wsimt.p, ps.data(), ps.size() * 4, cudaMemcpyHostToDevice));
+    PMP_CUDA(cudaMemcpy(d_wtc.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+
+    auto mk = [&](void *p, int C) {
+        Act a;
+        a.p = p; a.fmt = FMT_SPLIT; a.C = C; a.Cp = pad16(C); a.H = H; a.W = W; a.bf16 = bf;
+        return a;
+    };
+    Act in = mk(d_in.p, cin), res = mk(d_res.p, cout), mul = mk(d_mul.p, cout), out = mk(d_out.p, cout);
+    cudaStream_t s = nullptr;
+    f32_to_split_kernel<<<1024, 256, 0, s>>>((const float *)d_in32.p, in, B);
+    f32_to_split_kernel<<<1024, 256, 0, s>>>((const float *)d_res32.p, res, B);
+    f32_to_split_kernel<<<1024, 256, 0, s>>>((const float *)d_mul32.p, mul, B);
+    PMP_CUDA(cudaMemsetAsync(d_out.p, 0xFF, sp_out, s));
+    PMP_CUDA(cudaGetLastError());
+
+    cudaEvent_t e0, e1, e2, e3;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    // reference: SIMT conv on the same split inputs -> fp32 NCHW
+    SimtConvArgs sa;
+    sa.in = in;
+    sa.out.p = d_ref32.p; sa.out.fmt = FMT_F32; sa.out.C = sa.out.Cp = cout; sa.out.H = H; sa.out.W = W;
+    if (flags & 2) sa.res = res;
+    if (flags & 4) sa.mul = mul;
+    sa.w = (const float *)d_wsimt.p; sa.cin = cin; sa.cout = cout; sa.coutw = coutw;
+    sa.pad_t = sa.pad_l = ksize / 2; sa.Ho = H; sa.Wo = W; sa.relu = flags & 1; sa.pool = 1;
+    cudaEventRecord(e0, s);
+    int rc = conv_simt(h, sa, ksize, ksize, B, s);
+    cudaEventRecord(e1, s);
+    if (rc) return rc;
+    TcConvArgs ta;
+    ta.in = in; ta.out = out;
+    if (flags & 2) ta.res = res;
+    if (flags & 4) ta.mul = mul;
+    ta.w = (const uint16_t *)d_wtc.p; ta.cin_pad = cinp; ta.cout_pad = coutp; ta.ksize = ksize; ta.relu = flags & 1; ta.pool = 1;
+    pmp::g_tc_variant = (flags >> 8) & 0xFF;
+    rc = conv_tc(h, ta, B, s);          // warm-up (also first-launch overheads)
+    cudaEventRecord(e2, s);
+    if (!rc) rc = conv_tc(h, ta, B, s);
+    cudaEventRecord(e3, s);
+    pmp::g_tc_variant = 0;
+    if (rc) return rc;
+    split_to_f32_kernel<<<1024, 256, 0, s>>>(out, (float *)d_out32.p, B);
+    cudaError_t ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess) return cuda_fail(ce, "selftest sync", __FILE__, __LINE__);
+    float t_simt = 0, t_tc = 0;
+    cudaEventElapsedTime(&t_simt, e0, e1);
+    cudaEventElapsedTime(&t_tc, e2, e3);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    std::vector<float> got(n_out), want(n_out);
+    PMP_CUDA(cudaMemcpy(got.data(), d_out32.p, n_out * 4, cudaMemcpyDeviceToHost));
+    PMP_CUDA(cudaMemcpy(want.data(), d_ref32.p, n_out * 4, cudaMemcpyDeviceToHost));
+    double me = 0, am = 0;
+    size_t nbad = 0, first_bad = (size_t)-1;
+    for (size_t i = 0; i < n_out; i++) {
+        double e = fabs((double)got[i] - (double)want[i]);
+        if (!(e == e)) e = 1e30;
+        if (e > me) me = e;
+        if (fabs(want[i]) > am) am = fabs(want[i]);
+        if (e > 1e-3 * (1.0 + fabs(want[i]))) { nbad++; if (first_bad == (size_t)-1) first_bad = i; }
+    }
+    if ((flags & (1 << 16)) && nbad) {
+        fprintf(stderr, "[selftest] cin %d cout %d k %d hw %d B %d flags %x: %zu/%zu bad, max err %g (ref absmax %g)\n", cin,
+                cout, ksize, hw, B, flags, nbad, n_out, me, am);
+        // error map by (y, x) for image 0 / channel 0 and by channel at pixel (H/2, W/2)
+        int shown = 0;
+        for (size_t i = first_bad; i < n_out && shown < 12; i++) {
+            double e = fabs((double)got[i] - (double)want[i]);
+            if (e > 1e-3 * (1.0 + fabs(want[i])) || !(e == e)) {
+                int x = (int)(i % W), y = (int)((i / W) % H), c = (int)((i / ((size_t)W * H)) % cout), n = (int)(i / ((size_t)W * H * cout));
+                fprintf(stderr, "   n %d c %d y %d x %d: got %g want %g\n", n, c, y, x, got[i], want[i]);
+                shown++;
+            }
+        }
+        std::vector<int> by_y(H, 0), by_x(W, 0), by_c(cout, 0);
+        for (size_t i = 0; i < n_out; i++) {
+            double e = fabs((double)got[i] - (double)want[i]);
+            if (e > 1e-3 * (1.0 + fabs(want[i])) || !(e == e)) {
+                by_x[i % W]++; by_y[(i / W) % H]++; by_c[(i / ((size_t)W * H)) % cout]++;
+            }
+        }
+        fprintf(stderr, "   bad by y:");
+        for (int y = 0; y < H; y++) fprintf(stderr, " %d", by_y[y]);
+        fprintf(stderr, "\n   bad by x:");
+        for (int x = 0; x < W; x++) fprintf(stderr, " %d", by_x[x]);
+        fprintf(stderr, "\n   bad by c:");
+        for (int c = 0; c < cout; c++) fprintf(stderr, " %d", by_c[c]);
+        fprintf(stderr, "\n");
+    }
+    if (max_err) *max_err = me;
+    if (ref_absmax) *ref_absmax = am;
+    if (ms_tc) *ms_tc = t_tc;
+    if (ms_simt) *ms_simt = t_simt;
+    return PMP_OK;
+}
