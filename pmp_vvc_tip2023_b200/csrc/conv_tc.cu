@@ -30,7 +30,8 @@
 
 namespace pmp {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 352;
+constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_MAX_GROUPS = 8;
 constexpr uint32_t TC_SMEM_HEADER = 1024;
@@ -98,7 +99,7 @@ static inline void host_split(float w, bool bf16, uint16_t &hi, uint16_t &lo)
     }
 }
 
-// [tap][group][k8 (2)][n (2*cout_pad: hi couts then lo couts)][8 cin] 16-bit; w is the reference's [cout][cin][k][k] fp32
+// [group][tap][k8 (2)][n (2*cout_pad: hi couts then lo couts)][8 cin] 16-bit; w is the reference's [cout][cin][k][k] fp32
 void pack_tc_weights(const float *w, int cout, int cin, int ksize, int cin_pad, int cout_pad, bool bf16, uint16_t *dst)
 {
     const int groups = cin_pad / 16, N1 = 2 * cout_pad, taps = ksize * ksize;
@@ -110,7 +111,7 @@ void pack_tc_weights(const float *w, int cout, int cin, int ksize, int cin_pad, 
                         const int c = g * 16 + k8 * 8 + e;
                         uint16_t hi = 0, lo = 0;
                         if (n < cout && c < cin) host_split(w[((size_t)n * cin + c) * taps + t], bf16, hi, lo);
-                        const size_t base = (((size_t)t * groups + g) * 2 + k8) * N1 * 8;
+                        const size_t base = (((size_t)g * taps + t) * 2 + k8) * N1 * 8;
                         dst[base + (size_t)n * 8 + e] = hi;
                         dst[base + (size_t)(cout_pad + n) * 8 + e] = lo;
                     }
@@ -179,39 +180,141 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
 
 struct TcParams {
     const uint16_t *w;
     Act out, res, mul;
-    int H, W, P, k, pad, groups, MT, total_mt, N1, coutp, nstages;
+    int H, W, P, k, pad, groups, total_mt, tiles, N1, coutp, nstages, items;
     uint32_t plane_bytes, group_bytes, stage_bytes, tmem_cols, idesc1, idesc2;
-    int relu, variant;
+    int relu;
 };
 
+struct TileGeom { int n, mt_count, q0, row0, qoff; };
+
+__device__ __forceinline__ TileGeom tile_geom(const TcParams &p, int item)
+{
+    TileGeom t;
+    t.n = item / p.tiles;
+    const int tl = item - t.n * p.tiles;
+    const int mt_begin = (tl * p.total_mt) / p.tiles, mt_end = ((tl + 1) * p.total_mt) / p.tiles;
+    t.mt_count = mt_end - mt_begin;
+    t.q0 = mt_begin * 128;
+    t.row0 = t.q0 / p.P;
+    t.qoff = t.q0 - t.row0 * p.P;
+    return t;
+}
+
+__device__ __forceinline__ void unpack_split(const uint4 &H, const uint4 &L, bool bf, float v[8])
+{
+    const uint32_t hw[4] = {H.x, H.y, H.z, H.w}, lw[4] = {L.x, L.y, L.z, L.w};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        v[2 * e] = join16((uint16_t)(hw[e] & 0xffff), (uint16_t)(lw[e] & 0xffff), bf);
+        v[2 * e + 1] = join16((uint16_t)(hw[e] >> 16), (uint16_t)(lw[e] >> 16), bf);
+    }
+}
+
+// Epilogue of one M-tile for CH consecutive 8-channel chunks starting at chunk ch0 (one thread = one position).
+template <int CH>
+__device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t taddr, int ch0, int n, int r, int c, bool valid)
+{
+    const size_t plane = (size_t)p.H * p.W;
+    const size_t pix = (size_t)r * p.W + c;
+    uint4 rh[CH], rl[CH];
+    // residual / attention operands first: their latency overlaps the TMEM loads
+    if (p.res.p && valid) {
+        const uint4 *rb = reinterpret_cast<const uint4 *>(p.res.p) + (size_t)n * (p.res.Cp >> 2) * plane + pix;
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            const uint4 *q = rb + (size_t)split_plane(ch0 + j, 0) * plane;
+            rh[j] = ldg_stream(q);
+            rl[j] = ldg_stream(q + 2 * plane);
+        }
+    }
+    uint32_t hi[CH][8], lo[CH][8];
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+        tmem_ld8(taddr + 8 * (ch0 + j), hi[j]);
+        tmem_ld8(taddr + p.coutp + 8 * (ch0 + j), lo[j]);
+    }
+    tmem_wait_ld();
+    if (!valid) return;
+    const bool bf = p.out.bf16 != 0;
+    uint4 *ob = reinterpret_cast<uint4 *>(p.out.p) + (size_t)n * (p.out.Cp >> 2) * plane + pix;
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = __uint_as_float(hi[j][e]) + __uint_as_float(lo[j][e]);
+        if (p.res.p) {
+            float rv[8];
+            unpack_split(rh[j], rl[j], bf, rv);
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[e] += rv[e];
+        }
+        if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[e] = fmaxf(v[e], 0.f);
+        }
+        if (p.mul.p) {      // attention product: only the last conv of the two Att trunks, latency not hidden
+            const uint4 *q = reinterpret_cast<const uint4 *>(p.mul.p) + (size_t)n * (p.mul.Cp >> 2) * plane + pix +
+                             (size_t)split_plane(ch0 + j, 0) * plane;
+            float mv[8];
+            unpack_split(ldg_stream(q), ldg_stream(q + 2 * plane), bf, mv);
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[e] *= mv[e];
+        }
+        uint16_t h16[8], l16[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) split16(v[e], bf, h16[e], l16[e]);
+        uint4 Hh, Ll;
+        Hh.x = h16[0] | ((uint32_t)h16[1] << 16); Hh.y = h16[2] | ((uint32_t)h16[3] << 16);
+        Hh.z = h16[4] | ((uint32_t)h16[5] << 16); Hh.w = h16[6] | ((uint32_t)h16[7] << 16);
+        Ll.x = l16[0] | ((uint32_t)l16[1] << 16); Ll.y = l16[2] | ((uint32_t)l16[3] << 16);
+        Ll.z = l16[4] | ((uint32_t)l16[5] << 16); Ll.w = l16[6] | ((uint32_t)l16[7] << 16);
+        uint4 *q = ob + (size_t)split_plane(ch0 + j, 0) * plane;
+        q[0] = Hh;
+        q[2 * plane] = Ll;
+    }
+}
+
+// Persistent, warp-specialised: warp 0 weight producer, warp 1 MMA issuer, warp 2 activation producer + TMEM owner,
+// warps 3..10 epilogue (TMEM lane quarter = warp % 4, channel half = (warp - 3) / 4).
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-    // barrier slots: [0,8) act_full, [8,8+12) w_full, [24,24+12) w_empty, [40] acc_full
-    const uint32_t bar_act = smem_u32(bars), bar_wfull = smem_u32(bars + 8), bar_wempty = smem_u32(bars + 24),
-                   bar_acc = smem_u32(bars + 40);
+    // barrier slots: [0,8) act_full, [8,16) act_empty, [16,28) w_full, [28,40) w_empty, [40] acc_full, [41] acc_empty
+    const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + 8), bar_wfull = smem_u32(bars + 16),
+                   bar_wempty = smem_u32(bars + 28), bar_acc = smem_u32(bars + 40), bar_accempty = smem_u32(bars + 41);
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 512);
     uint8_t *act = smem + TC_SMEM_HEADER;
     uint8_t *ring = act + (size_t)p.groups * p.group_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.y;
-    const int mt0 = blockIdx.x * p.MT;
-    const int mt_count = (p.total_mt - mt0 < p.MT) ? (p.total_mt - mt0) : p.MT;
-    const int q0 = mt0 * 128;
-    const int row0 = q0 / p.P, qoff = q0 - row0 * p.P;
-    const int nst_total = p.k * p.k * p.groups;
+    const int taps = p.k * p.k;
 
     if (threadIdx.x == 0) {
-        for (int g = 0; g < p.groups; g++) mbar_init(bar_act + 8 * g, 1);
+        for (int g = 0; g < p.groups; g++) { mbar_init(bar_afull + 8 * g, 1); mbar_init(bar_aempty + 8 * g, 1); }
         for (int s = 0; s < p.nstages; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
         mbar_init(bar_acc, 1);
+        mbar_init(bar_accempty, TC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -226,86 +329,104 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
 
     if (warp == 0) {
         if (lane == 0) {
-            // ===== producer: activation halo tile (one box per 16-channel group), then the weight ring =====
-            for (int g = 0; g < p.groups; g++) {
-                mbar_expect_tx(bar_act + 8 * g, p.group_bytes);
-                tma_load_5d(smem_u32(act + (size_t)g * p.group_bytes), &tmap, bar_act + 8 * g, 0, -p.pad, row0 - p.pad,
-                            g * 4, n);
-            }
+            // ===== weight producer: one (group, tap) slab [2][N1][8] per ring stage, same order for every tile =====
             const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(p.w);
-            for (int it = 0; it < nst_total; it++) {
-                const int s = it % p.nstages;
-                const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
-                mbar_wait(bar_wempty + 8 * s, ph ^ 1u);
-                mbar_expect_tx(bar_wfull + 8 * s, p.stage_bytes);
-                bulk_g2s(smem_u32(ring + (size_t)s * p.stage_bytes), wsrc + (size_t)it * p.stage_bytes, p.stage_bytes,
-                         bar_wfull + 8 * s);
+            const int per_item = taps * p.groups;
+            uint32_t wst = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+                for (int it = 0; it < per_item; it++, wst++) {
+                    const uint32_t s = wst % (uint32_t)p.nstages, ph = (wst / (uint32_t)p.nstages) & 1u;
+                    mbar_wait(bar_wempty + 8 * s, ph ^ 1u);
+                    mbar_expect_tx(bar_wfull + 8 * s, p.stage_bytes);
+                    bulk_g2s(smem_u32(ring + (size_t)s * p.stage_bytes), wsrc + (size_t)it * p.stage_bytes, p.stage_bytes,
+                             bar_wfull + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {
+            // ===== activation producer: one TMA box per 16-channel group; buffer g is refilled for the next tile as
+            //       soon as the MMAs of group g of the current tile have drained it =====
+            uint32_t idx = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x, idx++) {
+                const TileGeom t = tile_geom(p, item);
+                for (int g = 0; g < p.groups; g++) {
+                    mbar_wait(bar_aempty + 8 * g, (idx & 1u) ^ 1u);
+                    mbar_expect_tx(bar_afull + 8 * g, p.group_bytes);
+                    tma_load_5d(smem_u32(act + (size_t)g * p.group_bytes), &tmap, bar_afull + 8 * g, 0, -p.pad,
+                                t.row0 - p.pad, g * 4, t.n);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
             const uint32_t act_s = smem_u32(act), ring_s = smem_u32(ring);
-            const uint32_t lboA = (p.variant & 1) ? 128u : p.plane_bytes, sboA = (p.variant & 1) ? p.plane_bytes : 128u;
-            const uint32_t lboB = (p.variant & 1) ? 128u : (uint32_t)p.N1 * 16u, sboB = (p.variant & 1) ? (uint32_t)p.N1 * 16u : 128u;
-            for (int it = 0; it < nst_total; it++) {
-                const int s = it % p.nstages;
-                const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
-                const int tap = it / p.groups, g = it - tap * p.groups;
-                const int ky = tap / p.k, kx = tap - ky * p.k;
-                if (tap == 0) mbar_wait(bar_act + 8 * g, 0);
-                mbar_wait(bar_wfull + 8 * s, ph);
+            const uint32_t lboB = (uint32_t)p.N1 * 16u;
+            uint32_t wst = 0, idx = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x, idx++) {
+                const TileGeom t = tile_geom(p, item);
+                mbar_wait(bar_accempty, (idx & 1u) ^ 1u);       // epilogue has drained the previous tile's accumulators
                 tc_fence_after();
-                const uint32_t a0 = act_s + (uint32_t)g * p.group_bytes + (uint32_t)(qoff + ky * p.P + kx) * 16u;
-                const uint64_t bdesc = umma_desc(ring_s + (uint32_t)s * p.stage_bytes, lboB, sboB);
-                for (int mt = 0; mt < mt_count; mt++) {
-                    const uint32_t a_hi = a0 + (uint32_t)mt * 2048u;
-                    const uint32_t d = tmem_base + (uint32_t)(mt * p.N1);
-                    umma_f16(d, umma_desc(a_hi, lboA, sboA), bdesc, p.idesc1, it > 0 ? 1u : 0u);
-                    umma_f16(d, umma_desc(a_hi + 2u * p.plane_bytes, lboA, sboA), bdesc, p.idesc2, 1u);
+                for (int g = 0; g < p.groups; g++) {
+                    mbar_wait(bar_afull + 8 * g, idx & 1u);
+                    for (int tap = 0; tap < taps; tap++, wst++) {
+                        const uint32_t s = wst % (uint32_t)p.nstages, ph = (wst / (uint32_t)p.nstages) & 1u;
+                        const int ky = tap / p.k, kx = tap - ky * p.k;
+                        mbar_wait(bar_wfull + 8 * s, ph);
+                        tc_fence_after();
+                        const uint32_t a0 = act_s + (uint32_t)g * p.group_bytes + (uint32_t)(t.qoff + ky * p.P + kx) * 16u;
+                        const uint64_t bdesc = umma_desc(ring_s + s * p.stage_bytes, lboB, 128u);
+                        const uint32_t acc = (g | tap) ? 1u : 0u;
+                        for (int mt = 0; mt < t.mt_count; mt++) {
+                            const uint32_t a_hi = a0 + (uint32_t)mt * 2048u;
+                            const uint32_t d = tmem_base + (uint32_t)(mt * p.N1);
+                            umma_f16(d, umma_desc(a_hi, p.plane_bytes, 128u), bdesc, p.idesc1, acc);
+                            umma_f16(d, umma_desc(a_hi + 2u * p.plane_bytes, p.plane_bytes, 128u), bdesc, p.idesc2, 1u);
+                        }
+                        umma_commit(bar_wempty + 8 * s);        // weight slot free once these MMAs have read it
+                    }
+                    umma_commit(bar_aempty + 8 * g);            // activation buffer g free for the next tile
                 }
-                umma_commit(bar_wempty + 8 * s);       // frees the weight slot once these MMAs have read it
+                umma_commit(bar_acc);                           // accumulators of this tile complete
             }
-            umma_commit(bar_acc);                       // accumulators complete
         }
-    } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-        mbar_wait(bar_acc, 0);
-        tc_fence_after();
-        const int quarter = warp & 3;
-        const int nchunk = p.coutp >> 3;
-        for (int mt = 0; mt < mt_count; mt++) {
-            const int pos = q0 + mt * 128 + quarter * 32 + lane;
-            const int r = pos / p.P, c = pos - r * p.P;
-            const bool valid = (c < p.W) && (r < p.H);
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * p.N1);
-            for (int j = 0; j < nchunk; j++) {
-                uint32_t hi[8], lo[8];
-                tmem_ld8(taddr + 8 * j, hi);
-                tmem_ld8(taddr + p.coutp + 8 * j, lo);
-                tmem_wait_ld();
-                if (!valid) continue;
-                float v[8];
-#pragma unroll
-                for (int e = 0; e < 8; e++) v[e] = __uint_as_float(hi[e]) + __uint_as_float(lo[e]);
-                if (p.res.p) {
-                    float rv[8];
-                    load_chunk_split(p.res, n, j, r, c, rv);
-#pragma unroll
-                    for (int e = 0; e < 8; e++) v[e] += rv[e];
+    } else if (warp >= 3) {
+        // ===== epilogue =====
+        const int quarter = warp & 3, half = (warp - 3) >> 2;
+        const int nchunk = p.coutp >> 3, chh = nchunk >> 1, ch0 = half * chh;
+        uint32_t idx = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x, idx++) {
+            const TileGeom t = tile_geom(p, item);
+            // while the MMAs run: pull this tile's residual / attention operand lines into L2
+            if ((p.res.p || p.mul.p) && (lane & 7) == 0) {
+                const size_t plane = (size_t)p.H * p.W;
+                for (int mt = 0; mt < t.mt_count; mt++) {
+                    const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
+                    const int r = pos / p.P, c = pos - r * p.P;
+                    if (c < p.W && r < p.H) {
+                        for (int j = 0; j < chh; j++) {
+                            const size_t o = ((size_t)t.n * (p.out.Cp >> 2) + split_plane(ch0 + j, 0)) * plane + (size_t)r * p.W + c;
+                            if (p.res.p) { prefetch_l2(reinterpret_cast<const uint4 *>(p.res.p) + o); prefetch_l2(reinterpret_cast<const uint4 *>(p.res.p) + o + 2 * plane); }
+                            if (p.mul.p) { prefetch_l2(reinterpret_cast<const uint4 *>(p.mul.p) + o); prefetch_l2(reinterpret_cast<const uint4 *>(p.mul.p) + o + 2 * plane); }
+                        }
+                    }
                 }
-                if (p.relu) {
-#pragma unroll
-                    for (int e = 0; e < 8; e++) v[e] = fmaxf(v[e], 0.f);
-                }
-                if (p.mul.p) {
-                    float mv[8];
-                    load_chunk_split(p.mul, n, j, r, c, mv);
-#pragma unroll
-                    for (int e = 0; e < 8; e++) v[e] *= mv[e];
-                }
-                store_chunk_split(p.out, n, j, r, c, v);
             }
+            mbar_wait(bar_acc, idx & 1u);
+            tc_fence_after();
+            for (int mt = 0; mt < t.mt_count; mt++) {
+                const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
+                const int r = pos / p.P, c = pos - r * p.P;
+                const bool valid = (c < p.W) && (r < p.H);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * p.N1);
+                if (chh == 4) epilogue_chunks<4>(p, taddr, ch0, t.n, r, c, valid);
+                else if (chh == 2) epilogue_chunks<2>(p, taddr, ch0, t.n, r, c, valid);
+                else epilogue_chunks<1>(p, taddr, ch0, t.n, r, c, valid);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_accempty);
         }
     }
     tc_fence_before();
@@ -338,8 +459,6 @@ static int get_encoder(Handle *h, EncodeTiledFn *fn)
     return PMP_OK;
 }
 
-static int g_tc_variant = 0;       // descriptor variant for the self test (0 = as designed)
-
 int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
 {
     if (B <= 0) return PMP_OK;
@@ -368,20 +487,21 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     }
     TcParams p;
     p.w = a.w; p.out = a.out; p.res = a.res; p.mul = a.mul;
-    p.H = H; p.W = W; p.P = g.P; p.k = a.ksize; p.pad = a.ksize / 2; p.groups = g.groups; p.MT = g.MT;
-    p.total_mt = g.total_mt; p.N1 = g.N1; p.coutp = g.coutp; p.nstages = g.nstages;
+    p.H = H; p.W = W; p.P = g.P; p.k = a.ksize; p.pad = a.ksize / 2; p.groups = g.groups;
+    p.total_mt = g.total_mt; p.tiles = g.tiles; p.N1 = g.N1; p.coutp = g.coutp; p.nstages = g.nstages;
+    p.items = g.tiles * B;
     p.plane_bytes = g.plane_bytes; p.group_bytes = g.group_bytes; p.stage_bytes = g.stage_bytes; p.tmem_cols = g.tmem_cols;
     const uint32_t fmt = a.in.bf16 ? 1u : 0u;
     const uint32_t idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 4) << 24);
     p.idesc1 = idesc_base | ((uint32_t)(g.N1 >> 3) << 17);
     p.idesc2 = idesc_base | ((uint32_t)(g.coutp >> 3) << 17);
-    p.relu = a.relu; p.variant = g_tc_variant;
+    p.relu = a.relu;
     static bool attr_set = false;
     if (!attr_set) {
         PMP_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
         attr_set = true;
     }
-    dim3 grid(g.tiles, B);
+    dim3 grid(p.items < h->num_sms ? p.items : h->num_sms);
     const double flops = 2.0 * B * H * W * (double)a.out.C * a.in.C * a.ksize * a.ksize;
     ProfScope ps(h, PROF_CONV_TC, s, flops, 0);
     conv_tc_kernel<<<grid, TC_THREADS, g.smem_bytes, s>>>(tmap, p);
@@ -559,12 +679,10 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     if (flags & 2) ta.res = res;
     if (flags & 4) ta.mul = mul;
     ta.w = (const uint16_t *)d_wtc.p; ta.cin_pad = cinp; ta.cout_pad = coutp; ta.ksize = ksize; ta.relu = flags & 1; ta.pool = 1;
-    pmp::g_tc_variant = (flags >> 8) & 0xFF;
     rc = conv_tc(h, ta, B, s);          // warm-up (also first-launch overheads)
     cudaEventRecord(e2, s);
     if (!rc) rc = conv_tc(h, ta, B, s);
     cudaEventRecord(e3, s);
-    pmp::g_tc_variant = 0;
     if (rc) return rc;
     split_to_f32_kernel<<<1024, 256, 0, s>>>(out, (float *)d_out32.p, B);
     cudaError_t ce = cudaStreamSynchronize(s);
