@@ -180,6 +180,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
 }
+__device__ __forceinline__ uint32_t elect_one_sync()
+{
+    uint32_t pred = 0, laneid = 0;
+    asm volatile("{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\telect.sync %%rx|%%px, %2;\n\t@%%px mov.s32 %1, 1;\n\tmov.s32 %0, %%rx;\n\t}"
+                 : "+r"(laneid), "+r"(pred) : "r"(0xFFFFFFFFu));
+    return pred;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -332,14 +339,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
             // ===== weight producer: one (group, tap) slab [2][N1][8] per ring stage, same order for every tile =====
             const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(p.w);
             const int per_item = taps * p.groups;
-            uint32_t wst = 0;
+            uint32_t s = 0, ph = 0;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-                for (int it = 0; it < per_item; it++, wst++) {
-                    const uint32_t s = wst % (uint32_t)p.nstages, ph = (wst / (uint32_t)p.nstages) & 1u;
+                const uint8_t *src = wsrc;
+                for (int it = 0; it < per_item; it++, src += p.stage_bytes) {
                     mbar_wait(bar_wempty + 8 * s, ph ^ 1u);
                     mbar_expect_tx(bar_wfull + 8 * s, p.stage_bytes);
-                    bulk_g2s(smem_u32(ring + (size_t)s * p.stage_bytes), wsrc + (size_t)it * p.stage_bytes, p.stage_bytes,
-                             bar_wfull + 8 * s);
+                    bulk_g2s(smem_u32(ring) + s * p.stage_bytes, src, p.stage_bytes, bar_wfull + 8 * s);
+                    if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -359,37 +366,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t act_s = smem_u32(act), ring_s = smem_u32(ring);
-            const uint32_t lboB = (uint32_t)p.N1 * 16u;
-            uint32_t wst = 0, idx = 0;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x, idx++) {
-                const TileGeom t = tile_geom(p, item);
-                mbar_wait(bar_accempty, (idx & 1u) ^ 1u);       // epilogue has drained the previous tile's accumulators
-                tc_fence_after();
-                for (int g = 0; g < p.groups; g++) {
-                    mbar_wait(bar_afull + 8 * g, idx & 1u);
-                    for (int tap = 0; tap < taps; tap++, wst++) {
-                        const uint32_t s = wst % (uint32_t)p.nstages, ph = (wst / (uint32_t)p.nstages) & 1u;
-                        const int ky = tap / p.k, kx = tap - ky * p.k;
+        // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues; keep it lean, it
+        //       paces the tensor pipe.  Descriptors are linear in the start address (16-byte units, low 14 bits). =====
+        const uint64_t desc_c = ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);             // SBO 128, version 1
+        const uint64_t adesc_c = desc_c | ((uint64_t)(p.plane_bytes >> 4) << 16);                // LBO = plane stride
+        const uint64_t bdesc_c = desc_c | ((uint64_t)(((uint32_t)p.N1 * 16u) >> 4) << 16);       // LBO = N1 rows
+        const uint32_t act16 = smem_u32(act) >> 4, ring16 = smem_u32(ring) >> 4;
+        const uint32_t group16 = p.group_bytes >> 4, stage16 = p.stage_bytes >> 4, lo16 = (2u * p.plane_bytes) >> 4;
+        const uint32_t idesc1 = p.idesc1, idesc2 = p.idesc2, N1 = (uint32_t)p.N1;
+        const int K = p.k, P = p.P, NS = p.nstages, G = p.groups;
+        uint32_t s = 0, ph = 0, idx = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x, idx++) {
+            const TileGeom t = tile_geom(p, item);
+            const int mtc = t.mt_count;
+            mbar_wait(bar_accempty, (idx & 1u) ^ 1u);           // epilogue has drained the previous tile's accumulators
+            tc_fence_after();
+            uint32_t acc = 0;
+            for (int g = 0; g < G; g++) {
+                mbar_wait(bar_afull + 8 * g, idx & 1u);
+                const uint32_t ag = act16 + (uint32_t)g * group16 + (uint32_t)t.qoff;
+                for (int ky = 0; ky < K; ky++) {
+                    for (int kx = 0; kx < K; kx++) {
                         mbar_wait(bar_wfull + 8 * s, ph);
                         tc_fence_after();
-                        const uint32_t a0 = act_s + (uint32_t)g * p.group_bytes + (uint32_t)(t.qoff + ky * p.P + kx) * 16u;
-                        const uint64_t bdesc = umma_desc(ring_s + s * p.stage_bytes, lboB, 128u);
-                        const uint32_t acc = (g | tap) ? 1u : 0u;
-                        for (int mt = 0; mt < t.mt_count; mt++) {
-                            const uint32_t a_hi = a0 + (uint32_t)mt * 2048u;
-                            const uint32_t d = tmem_base + (uint32_t)(mt * p.N1);
-                            umma_f16(d, umma_desc(a_hi, p.plane_bytes, 128u), bdesc, p.idesc1, acc);
-                            umma_f16(d, umma_desc(a_hi + 2u * p.plane_bytes, p.plane_bytes, 128u), bdesc, p.idesc2, 1u);
+                        if (elect_one_sync()) {
+                            const uint64_t ad = adesc_c | (uint64_t)(ag + (uint32_t)(ky * P + kx));
+                            const uint64_t bd = bdesc_c | (uint64_t)(ring16 + s * stage16);
+#pragma unroll
+                            for (int mt = 0; mt < 4; mt++) {
+                                if (mt < mtc) {
+                                    umma_f16(tmem_base + (uint32_t)mt * N1, ad + (uint64_t)(mt * 128), bd, idesc1, acc);
+                                    umma_f16(tmem_base + (uint32_t)mt * N1, ad + (uint64_t)(mt * 128 + lo16), bd, idesc2, 1u);
+                                }
+                            }
+                            umma_commit(bar_wempty + 8 * s);    // weight slot free once these MMAs have read it
                         }
-                        umma_commit(bar_wempty + 8 * s);        // weight slot free once these MMAs have read it
+                        __syncwarp();
+                        acc = 1u;
+                        if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
                     }
-                    umma_commit(bar_aempty + 8 * g);            // activation buffer g free for the next tile
                 }
-                umma_commit(bar_acc);                           // accumulators of this tile complete
+                if (elect_one_sync()) umma_commit(bar_aempty + 8 * g);      // activation buffer g free for the next tile
+                __syncwarp();
             }
+            if (elect_one_sync()) umma_commit(bar_acc);                     // accumulators of this tile complete
+            __syncwarp();
         }
     } else if (warp >= 3) {
         // ===== epilogue =====
