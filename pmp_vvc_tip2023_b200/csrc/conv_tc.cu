@@ -30,7 +30,8 @@
 
 namespace pmp {
 
-constexpr int TC_THREADS = 352;
+constexpr int TC_THREADS = 448;
+constexpr int TC_MMA_WARPS = 4;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_MAX_GROUPS = 8;
@@ -226,13 +227,42 @@ __device__ __forceinline__ TileGeom tile_geom(const TcParams &p, int item)
     return t;
 }
 
+// packed pair versions of split16 / join16 (tensor.cuh): identical arithmetic, two elements per instruction
+__device__ __forceinline__ void split2(float a, float b, bool bf, uint32_t &hi, uint32_t &lo)
+{
+    if (bf) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        float2 hf = __bfloat1622float2(h);
+        __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+        hi = *reinterpret_cast<uint32_t *>(&h); lo = *reinterpret_cast<uint32_t *>(&l);
+    } else {
+        a = fminf(fmaxf(a, -65504.f), 65504.f);
+        b = fminf(fmaxf(b, -65504.f), 65504.f);
+        __half2 h = __floats2half2_rn(a, b);
+        float2 hf = __half22float2(h);
+        __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+        hi = *reinterpret_cast<uint32_t *>(&h); lo = *reinterpret_cast<uint32_t *>(&l);
+    }
+}
+__device__ __forceinline__ float2 join2(uint32_t hi, uint32_t lo, bool bf)
+{
+    float2 h, l;
+    if (bf) {
+        h = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&hi));
+        l = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&lo));
+    } else {
+        h = __half22float2(*reinterpret_cast<__half2 *>(&hi));
+        l = __half22float2(*reinterpret_cast<__half2 *>(&lo));
+    }
+    return make_float2(h.x + l.x, h.y + l.y);
+}
 __device__ __forceinline__ void unpack_split(const uint4 &H, const uint4 &L, bool bf, float v[8])
 {
     const uint32_t hw[4] = {H.x, H.y, H.z, H.w}, lw[4] = {L.x, L.y, L.z, L.w};
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-        v[2 * e] = join16((uint16_t)(hw[e] & 0xffff), (uint16_t)(lw[e] & 0xffff), bf);
-        v[2 * e + 1] = join16((uint16_t)(hw[e] >> 16), (uint16_t)(lw[e] >> 16), bf);
+        const float2 t = join2(hw[e], lw[e], bf);
+        v[2 * e] = t.x; v[2 * e + 1] = t.y;
     }
 }
 
@@ -243,7 +273,7 @@ __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t tadd
     const size_t plane = (size_t)p.H * p.W;
     const size_t pix = (size_t)r * p.W + c;
     uint4 rh[CH], rl[CH];
-    // residual / attention operands first: their latency overlaps the TMEM loads
+    // residual operand first: its latency overlaps the TMEM loads
     if (p.res.p && valid) {
         const uint4 *rb = reinterpret_cast<const uint4 *>(p.res.p) + (size_t)n * (p.res.Cp >> 2) * plane + pix;
 #pragma unroll
@@ -253,30 +283,30 @@ __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t tadd
             rl[j] = ldg_stream(q + 2 * plane);
         }
     }
-    uint32_t hi[CH][8], lo[CH][8];
+    float v[CH][8];
 #pragma unroll
-    for (int j = 0; j < CH; j++) {
-        tmem_ld8(taddr + 8 * (ch0 + j), hi[j]);
-        tmem_ld8(taddr + p.coutp + 8 * (ch0 + j), lo[j]);
+    for (int j = 0; j < CH; j++) {         // per chunk: keeps the transient register footprint at 16 (TMEM latency is short)
+        uint32_t hi[8], lo[8];
+        tmem_ld8(taddr + 8 * (ch0 + j), hi);
+        tmem_ld8(taddr + p.coutp + 8 * (ch0 + j), lo);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[j][e] = __uint_as_float(hi[e]) + __uint_as_float(lo[e]);
     }
-    tmem_wait_ld();
     if (!valid) return;
     const bool bf = p.out.bf16 != 0;
     uint4 *ob = reinterpret_cast<uint4 *>(p.out.p) + (size_t)n * (p.out.Cp >> 2) * plane + pix;
 #pragma unroll
     for (int j = 0; j < CH; j++) {
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; e++) v[e] = __uint_as_float(hi[j][e]) + __uint_as_float(lo[j][e]);
         if (p.res.p) {
             float rv[8];
             unpack_split(rh[j], rl[j], bf, rv);
 #pragma unroll
-            for (int e = 0; e < 8; e++) v[e] += rv[e];
+            for (int e = 0; e < 8; e++) v[j][e] += rv[e];
         }
         if (p.relu) {
 #pragma unroll
-            for (int e = 0; e < 8; e++) v[e] = fmaxf(v[e], 0.f);
+            for (int e = 0; e < 8; e++) v[j][e] = fmaxf(v[j][e], 0.f);
         }
         if (p.mul.p) {      // attention product: only the last conv of the two Att trunks, latency not hidden
             const uint4 *q = reinterpret_cast<const uint4 *>(p.mul.p) + (size_t)n * (p.mul.Cp >> 2) * plane + pix +
@@ -284,30 +314,28 @@ __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t tadd
             float mv[8];
             unpack_split(ldg_stream(q), ldg_stream(q + 2 * plane), bf, mv);
 #pragma unroll
-            for (int e = 0; e < 8; e++) v[e] *= mv[e];
+            for (int e = 0; e < 8; e++) v[j][e] *= mv[e];
         }
-        uint16_t h16[8], l16[8];
-#pragma unroll
-        for (int e = 0; e < 8; e++) split16(v[e], bf, h16[e], l16[e]);
         uint4 Hh, Ll;
-        Hh.x = h16[0] | ((uint32_t)h16[1] << 16); Hh.y = h16[2] | ((uint32_t)h16[3] << 16);
-        Hh.z = h16[4] | ((uint32_t)h16[5] << 16); Hh.w = h16[6] | ((uint32_t)h16[7] << 16);
-        Ll.x = l16[0] | ((uint32_t)l16[1] << 16); Ll.y = l16[2] | ((uint32_t)l16[3] << 16);
-        Ll.z = l16[4] | ((uint32_t)l16[5] << 16); Ll.w = l16[6] | ((uint32_t)l16[7] << 16);
+        split2(v[j][0], v[j][1], bf, Hh.x, Ll.x);
+        split2(v[j][2], v[j][3], bf, Hh.y, Ll.y);
+        split2(v[j][4], v[j][5], bf, Hh.z, Ll.z);
+        split2(v[j][6], v[j][7], bf, Hh.w, Ll.w);
         uint4 *q = ob + (size_t)split_plane(ch0 + j, 0) * plane;
         q[0] = Hh;
         q[2 * plane] = Ll;
     }
 }
 
-// Persistent, warp-specialised: warp 0 weight producer, warp 1 MMA issuer, warp 2 activation producer + TMEM owner,
-// warps 3..10 epilogue (TMEM lane quarter = warp % 4, channel half = (warp - 3) / 4).
+// Persistent, warp-specialised: warp 0 weight producer, warp 1 activation producer + TMEM owner, warps 2..5 MMA issuers
+// (one per M-tile of the CTA tile: a single issuing thread cannot keep the tensor pipe fed), warps 6..13 epilogue
+// (TMEM lane quarter = warp % 4, channel half = (warp - 6) / 4).
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-    // barrier slots: [0,8) act_full, [8,16) act_empty, [16,28) w_full, [28,40) w_empty, [40] acc_full, [41] acc_empty
+    // barrier slots: [0,8) act_full, [8,16) act_empty, [16,28) w_full, [28,40) w_empty, [40] acc_full, [41,45) acc_empty per M-tile
     const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + 8), bar_wfull = smem_u32(bars + 16),
                    bar_wempty = smem_u32(bars + 28), bar_acc = smem_u32(bars + 40), bar_accempty = smem_u32(bars + 41);
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 512);
@@ -318,13 +346,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
     const int taps = p.k * p.k;
 
     if (threadIdx.x == 0) {
-        for (int g = 0; g < p.groups; g++) { mbar_init(bar_afull + 8 * g, 1); mbar_init(bar_aempty + 8 * g, 1); }
-        for (int s = 0; s < p.nstages; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
-        mbar_init(bar_acc, 1);
-        mbar_init(bar_accempty, TC_EPI_WARPS);
+        for (int g = 0; g < p.groups; g++) { mbar_init(bar_afull + 8 * g, 1); mbar_init(bar_aempty + 8 * g, TC_MMA_WARPS); }
+        for (int s = 0; s < p.nstages; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, TC_MMA_WARPS); }
+        mbar_init(bar_acc, TC_MMA_WARPS);
+        for (int m = 0; m < 4; m++) mbar_init(bar_accempty + 8 * m, TC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
+    if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + 512)),
                      "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -350,7 +378,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
                 }
             }
         }
-    } else if (warp == 2) {
+    } else if (warp == 1) {
         if (lane == 0) {
             // ===== activation producer: one TMA box per 16-channel group; buffer g is refilled for the next tile as
             //       soon as the MMAs of group g of the current tile have drained it =====
@@ -365,21 +393,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues; keep it lean, it
-        //       paces the tensor pipe.  Descriptors are linear in the start address (16-byte units, low 14 bits). =====
+    } else if (warp < 2 + TC_MMA_WARPS) {
+        // ===== MMA issuers: warp 2+m owns M-tile m (accumulator columns [m*N1, (m+1)*N1)).  The whole warp runs the
+        //       warp-uniform loop and one elected lane issues.  Descriptors are linear in the start address (16-byte
+        //       units in the low 14 bits), so the constant parts are built once. =====
+        const int m = warp - 2;
         const uint64_t desc_c = ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);             // SBO 128, version 1
         const uint64_t adesc_c = desc_c | ((uint64_t)(p.plane_bytes >> 4) << 16);                // LBO = plane stride
         const uint64_t bdesc_c = desc_c | ((uint64_t)(((uint32_t)p.N1 * 16u) >> 4) << 16);       // LBO = N1 rows
-        const uint32_t act16 = smem_u32(act) >> 4, ring16 = smem_u32(ring) >> 4;
+        const uint32_t act16 = (smem_u32(act) >> 4) + (uint32_t)m * 128u, ring16 = smem_u32(ring) >> 4;
         const uint32_t group16 = p.group_bytes >> 4, stage16 = p.stage_bytes >> 4, lo16 = (2u * p.plane_bytes) >> 4;
-        const uint32_t idesc1 = p.idesc1, idesc2 = p.idesc2, N1 = (uint32_t)p.N1;
+        const uint32_t idesc1 = p.idesc1, idesc2 = p.idesc2;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(m * p.N1);
         const int K = p.k, P = p.P, NS = p.nstages, G = p.groups;
         uint32_t s = 0, ph = 0, idx = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, idx++) {
             const TileGeom t = tile_geom(p, item);
-            const int mtc = t.mt_count;
-            mbar_wait(bar_accempty, (idx & 1u) ^ 1u);           // epilogue has drained the previous tile's accumulators
+            const bool mine = m < t.mt_count;
+            mbar_wait(bar_accempty + 8 * m, (idx & 1u) ^ 1u);   // epilogue has drained this M-tile's accumulator
             tc_fence_after();
             uint32_t acc = 0;
             for (int g = 0; g < G; g++) {
@@ -390,31 +421,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
                         mbar_wait(bar_wfull + 8 * s, ph);
                         tc_fence_after();
                         if (elect_one_sync()) {
-                            const uint64_t ad = adesc_c | (uint64_t)(ag + (uint32_t)(ky * P + kx));
-                            const uint64_t bd = bdesc_c | (uint64_t)(ring16 + s * stage16);
-#pragma unroll
-                            for (int mt = 0; mt < 4; mt++) {
-                                if (mt < mtc) {
-                                    umma_f16(tmem_base + (uint32_t)mt * N1, ad + (uint64_t)(mt * 128), bd, idesc1, acc);
-                                    umma_f16(tmem_base + (uint32_t)mt * N1, ad + (uint64_t)(mt * 128 + lo16), bd, idesc2, 1u);
-                                }
+                            if (mine) {
+                                const uint64_t ad = adesc_c | (uint64_t)(ag + (uint32_t)(ky * P + kx));
+                                const uint64_t bd = bdesc_c | (uint64_t)(ring16 + s * stage16);
+                                umma_f16(d_tmem, ad, bd, idesc1, acc);
+                                umma_f16(d_tmem, ad + (uint64_t)lo16, bd, idesc2, 1u);
+                                umma_commit(bar_wempty + 8 * s);        // weight slot free once these MMAs have read it
+                            } else {
+                                mbar_arrive(bar_wempty + 8 * s);
                             }
-                            umma_commit(bar_wempty + 8 * s);    // weight slot free once these MMAs have read it
                         }
                         __syncwarp();
                         acc = 1u;
                         if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
                     }
                 }
-                if (elect_one_sync()) umma_commit(bar_aempty + 8 * g);      // activation buffer g free for the next tile
+                if (elect_one_sync()) {                          // activation buffer g free for the next tile
+                    if (mine) umma_commit(bar_aempty + 8 * g);
+                    else mbar_arrive(bar_aempty + 8 * g);
+                }
                 __syncwarp();
             }
-            if (elect_one_sync()) umma_commit(bar_acc);                     // accumulators of this tile complete
+            if (elect_one_sync()) {                              // accumulators of this tile complete
+                if (mine) umma_commit(bar_acc);
+                else mbar_arrive(bar_acc);
+            }
             __syncwarp();
         }
-    } else if (warp >= 3) {
+    } else {
         // ===== epilogue =====
-        const int quarter = warp & 3, half = (warp - 3) >> 2;
+        const int quarter = warp & 3, half = (warp - 2 - TC_MMA_WARPS) >> 2;
         const int nchunk = p.coutp >> 3, chh = nchunk >> 1, ch0 = half * chh;
         uint32_t idx = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, idx++) {
@@ -442,17 +478,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
                 const bool valid = (c < p.W) && (r < p.H);
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * p.N1);
                 if (chh == 4) epilogue_chunks<4>(p, taddr, ch0, t.n, r, c, valid);
-                else if (chh == 2) epilogue_chunks<2>(p, taddr, ch0, t.n, r, c, valid);
-                else epilogue_chunks<1>(p, taddr, ch0, t.n, r, c, valid);
+                else
+                    for (int j = 0; j < chh; j++) epilogue_chunks<1>(p, taddr, ch0 + j, t.n, r, c, valid);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_accempty + 8 * mt);      // this M-tile's accumulator may be overwritten
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_accempty);
+            // M-tiles this tile did not use still owe their issuer warp an arrival
+            for (int mt = t.mt_count; mt < 4; mt++) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_accempty + 8 * mt);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
 }
