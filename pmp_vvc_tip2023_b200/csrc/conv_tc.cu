@@ -142,11 +142,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) {}
 }
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int c0, int c1, int c2,
+                                            int c3)
 {
-    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
@@ -388,7 +388,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
                 for (int g = 0; g < p.groups; g++) {
                     mbar_wait(bar_aempty + 8 * g, (idx & 1u) ^ 1u);
                     mbar_expect_tx(bar_afull + 8 * g, p.group_bytes);
-                    tma_load_5d(smem_u32(act + (size_t)g * p.group_bytes), &tmap, bar_afull + 8 * g, 0, -p.pad,
+                    tma_load_4d(smem_u32(act + (size_t)g * p.group_bytes), &tmap, bar_afull + 8 * g, -2 * p.pad,
                                 t.row0 - p.pad, g * 4, t.n);
                 }
             }
@@ -536,11 +536,14 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     if (rc) return rc;
     CUtensorMap tmap;
     const cuuint64_t planes = (cuuint64_t)a.cin_pad / 4;
-    cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, planes, (cuuint64_t)B};
-    cuuint64_t gstr[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, planes * H * W * 16};
-    cuuint32_t box[5] = {8, (cuuint32_t)g.P, (cuuint32_t)g.Rbox, 4, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, a.in.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    // 8-byte elements: a pixel's 8-channel unit is two elements, so the inner box dimension is a whole P-pixel row
+    // (P*16 contiguous bytes) instead of one 16-byte unit (a 16-byte inner dimension makes every request pull a 32-byte
+    // sector: measured 2x L2->SM traffic)
+    cuuint64_t gdim[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, planes, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, planes * H * W * 16};
+    cuuint32_t box[4] = {(cuuint32_t)g.P * 2, (cuuint32_t)g.Rbox, 4, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, a.in.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) for W %d H %d planes %d B %d box %d x %d", (int)cr, W, H, (int)planes, B,
