@@ -5,10 +5,11 @@
 // Split precision (single-pass 16-bit operands miss the 1e-2 parity bar): activations and
 // weights are stored as hi + lo 16-bit pairs and three products are accumulated,
 //   a_hi*w_hi + a_hi*w_lo + a_lo*w_hi        (error ~ a_lo*w_lo ~ 2^-22 relative with fp16),
-// as two tcgen05.mma per K=16 step: (a_hi) x [w_hi | w_lo] with N = 2*Cout into columns [0, 2*Cout) of the M-tile's
-// accumulator, then (a_lo) x [w_hi] with N = Cout into columns [0, Cout).  The epilogue adds the two column halves.
+// as three tcgen05.mma (N = Cout) per K=16 step into the same Cout accumulator columns.  (Stacking [w_hi | w_lo] along
+// N saves shared-memory operand reads but needs 2*Cout columns per M-tile; measured, the kernel is bound by issue
+// latency and the TMEM drain rather than by operand bandwidth, so the columns are spent on double buffering instead.)
 //
-// Tiling ("halo-resident linear tile"): a CTA owns up to 4 M-tiles of 128 consecutive positions of ONE image, counted on
+// Tiling ("halo-resident linear tile"): a CTA tile is up to 4 M-tiles of 128 consecutive positions of ONE image, counted on
 // the zero-padded pitch P = W + k - 1.  One TMA box per 16-channel group (8 x P x rows x 4 planes) brings the halo tile
 // of the FMT_SPLIT activation (tensor.cuh) into shared memory exactly in the no-swizzle K-major UMMA layout, TMA's
 // out-of-bounds zero fill providing the convolution's zero padding.  Because the tile is linear on pitch P, the A
@@ -61,14 +62,14 @@ static bool tc_geometry(int cin_pad, int cout_pad, int k, int H, int W, TcGeom &
         if (rbox > 256) continue;
         uint32_t plane = (uint32_t)rbox * g.P * 16;
         uint32_t act = plane * 4 * g.groups;
-        if (TC_SMEM_HEADER + act + 4 * g.stage_bytes > TC_SMEM_MAX) continue;
+        if (TC_SMEM_HEADER + act + (uint32_t)(k + 3) * g.stage_bytes > TC_SMEM_MAX) continue;   // ring >= one filter row + 2
         int ns = (int)((TC_SMEM_MAX - TC_SMEM_HEADER - act) / g.stage_bytes);
         if (ns > TC_MAX_STAGES) ns = TC_MAX_STAGES;
         g.MT = mt; g.Rbox = rbox; g.plane_bytes = plane; g.group_bytes = plane * 4; g.act_bytes = act;
         g.nstages = ns;
         g.smem_bytes = TC_SMEM_HEADER + act + ns * g.stage_bytes;
         g.tiles = (g.total_mt + mt - 1) / mt;
-        uint32_t cols = (uint32_t)mt * g.N1, pc = 32;
+        uint32_t cols = 8u * g.coutp, pc = 32;     // 2 accumulator buffers x 4 M-tiles x Cout columns
         while (pc < cols) pc <<= 1;
         g.tmem_cols = pc;
         return pc <= 512;
@@ -285,13 +286,12 @@ __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t tadd
     }
     float v[CH][8];
 #pragma unroll
-    for (int j = 0; j < CH; j++) {         // per chunk: keeps the transient register footprint at 16 (TMEM latency is short)
-        uint32_t hi[8], lo[8];
-        tmem_ld8(taddr + 8 * (ch0 + j), hi);
-        tmem_ld8(taddr + p.coutp + 8 * (ch0 + j), lo);
+    for (int j = 0; j < CH; j++) {         // per chunk: small transient register footprint (TMEM latency is short)
+        uint32_t a[8];
+        tmem_ld8(taddr + 8 * (ch0 + j), a);
         tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 8; e++) v[j][e] = __uint_as_float(hi[e]) + __uint_as_float(lo[e]);
+        for (int e = 0; e < 8; e++) v[j][e] = __uint_as_float(a[e]);
     }
     if (!valid) return;
     const bool bf = p.out.bf16 != 0;
@@ -335,9 +335,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-    // barrier slots: [0,8) act_full, [8,16) act_empty, [16,28) w_full, [28,40) w_empty, [40] acc_full, [41,45) acc_empty per M-tile
+    // barrier slots: [0,8) act_full, [8,16) act_empty, [16,28) w_full, [28,40) w_empty, [40,42) acc_full per accumulator buffer, [42,50) acc_empty per accumulator (buffer, M-tile)
     const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + 8), bar_wfull = smem_u32(bars + 16),
-                   bar_wempty = smem_u32(bars + 28), bar_acc = smem_u32(bars + 40), bar_accempty = smem_u32(bars + 41);
+                   bar_wempty = smem_u32(bars + 28), bar_acc = smem_u32(bars + 40), bar_accempty = smem_u32(bars + 42);
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 512);
     uint8_t *act = smem + TC_SMEM_HEADER;
     uint8_t *ring = act + (size_t)p.groups * p.group_bytes;
@@ -349,7 +349,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
         for (int g = 0; g < p.groups; g++) { mbar_init(bar_afull + 8 * g, 1); mbar_init(bar_aempty + 8 * g, TC_MMA_WARPS); }
         for (int s = 0; s < p.nstages; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, TC_MMA_WARPS); }
         mbar_init(bar_acc, TC_MMA_WARPS);
-        for (int m = 0; m < 4; m++) mbar_init(bar_accempty + 8 * m, TC_EPI_WARPS);
+        mbar_init(bar_acc + 8, TC_MMA_WARPS);
+        for (int m = 0; m < 8; m++) mbar_init(bar_accempty + 8 * m, TC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -403,38 +404,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
         const uint64_t bdesc_c = desc_c | ((uint64_t)(((uint32_t)p.N1 * 16u) >> 4) << 16);       // LBO = N1 rows
         const uint32_t act16 = (smem_u32(act) >> 4) + (uint32_t)m * 128u, ring16 = smem_u32(ring) >> 4;
         const uint32_t group16 = p.group_bytes >> 4, stage16 = p.stage_bytes >> 4, lo16 = (2u * p.plane_bytes) >> 4;
-        const uint32_t idesc1 = p.idesc1, idesc2 = p.idesc2;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(m * p.N1);
+        const uint32_t idesc = p.idesc2, wlo16 = (uint32_t)p.coutp;                              // w_lo rows follow w_hi rows
         const int K = p.k, P = p.P, NS = p.nstages, G = p.groups;
         uint32_t s = 0, ph = 0, idx = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, idx++) {
             const TileGeom t = tile_geom(p, item);
+            const uint32_t buf = idx & 1u;                      // tiles alternate between the two accumulator buffers
             const bool mine = m < t.mt_count;
-            mbar_wait(bar_accempty + 8 * m, (idx & 1u) ^ 1u);   // epilogue has drained this M-tile's accumulator
+            const uint32_t d_tmem = tmem_base + (buf * 4u + (uint32_t)m) * (uint32_t)p.coutp;
+            mbar_wait(bar_accempty + 8 * (buf * 4 + m), ((idx >> 1) & 1u) ^ 1u);    // epilogue drained it (tile idx-2)
             tc_fence_after();
             uint32_t acc = 0;
             for (int g = 0; g < G; g++) {
                 mbar_wait(bar_afull + 8 * g, idx & 1u);
                 const uint32_t ag = act16 + (uint32_t)g * group16 + (uint32_t)t.qoff;
                 for (int ky = 0; ky < K; ky++) {
-                    for (int kx = 0; kx < K; kx++) {
-                        mbar_wait(bar_wfull + 8 * s, ph);
-                        tc_fence_after();
-                        if (elect_one_sync()) {
-                            if (mine) {
-                                const uint64_t ad = adesc_c | (uint64_t)(ag + (uint32_t)(ky * P + kx));
-                                const uint64_t bd = bdesc_c | (uint64_t)(ring16 + s * stage16);
-                                umma_f16(d_tmem, ad, bd, idesc1, acc);
-                                umma_f16(d_tmem, ad + (uint64_t)lo16, bd, idesc2, 1u);
-                                umma_commit(bar_wempty + 8 * s);        // weight slot free once these MMAs have read it
-                            } else {
-                                mbar_arrive(bar_wempty + 8 * s);
+                    // one filter row = K weight slabs: probe all their barriers back to back, then spin on stragglers
+                    uint32_t sj[5], pj[5];
+                    bool ok[5];
+                    {
+                        uint32_t s2 = s, ph2 = ph;
+#pragma unroll
+                        for (int j = 0; j < 5; j++) {
+                            if (j < K) {
+                                sj[j] = s2; pj[j] = ph2;
+                                ok[j] = mbar_try_wait(bar_wfull + 8 * s2, ph2);
+                                if (++s2 == (uint32_t)NS) { s2 = 0; ph2 ^= 1u; }
                             }
                         }
-                        __syncwarp();
-                        acc = 1u;
-                        if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
+                        s = s2; ph = ph2;
                     }
+#pragma unroll
+                    for (int j = 0; j < 5; j++)
+                        if (j < K) while (!ok[j]) ok[j] = mbar_try_wait(bar_wfull + 8 * sj[j], pj[j]);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        if (mine) {
+                            const uint64_t ad0 = adesc_c | (uint64_t)(ag + (uint32_t)(ky * P));
+#pragma unroll
+                            for (int j = 0; j < 5; j++) {
+                                if (j < K) {
+                                    const uint64_t ad = ad0 + (uint64_t)j;
+                                    const uint64_t bd = bdesc_c | (uint64_t)(ring16 + sj[j] * stage16);
+                                    umma_f16(d_tmem, ad, bd, idesc, acc);                       // a_hi * w_hi
+                                    umma_f16(d_tmem, ad, bd + (uint64_t)wlo16, idesc, 1u);      // a_hi * w_lo
+                                    umma_f16(d_tmem, ad + (uint64_t)lo16, bd, idesc, 1u);       // a_lo * w_hi
+                                    umma_commit(bar_wempty + 8 * sj[j]);                        // slab free when read
+                                    acc = 1u;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 5; j++)
+                                if (j < K) mbar_arrive(bar_wempty + 8 * sj[j]);
+                        }
+                    }
+                    __syncwarp();
+                    acc = 1u;
                 }
                 if (elect_one_sync()) {                          // activation buffer g free for the next tile
                     if (mine) umma_commit(bar_aempty + 8 * g);
@@ -443,8 +469,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
                 __syncwarp();
             }
             if (elect_one_sync()) {                              // accumulators of this tile complete
-                if (mine) umma_commit(bar_acc);
-                else mbar_arrive(bar_acc);
+                if (mine) umma_commit(bar_acc + 8 * buf);
+                else mbar_arrive(bar_acc + 8 * buf);
             }
             __syncwarp();
         }
@@ -470,24 +496,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
                     }
                 }
             }
-            mbar_wait(bar_acc, idx & 1u);
+            const uint32_t buf = idx & 1u;
+            mbar_wait(bar_acc + 8 * buf, (idx >> 1) & 1u);
             tc_fence_after();
             for (int mt = 0; mt < t.mt_count; mt++) {
                 const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
                 const int r = pos / p.P, c = pos - r * p.P;
                 const bool valid = (c < p.W) && (r < p.H);
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * p.N1);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (4u * buf + (uint32_t)mt) * (uint32_t)p.coutp;
                 if (chh == 4) epilogue_chunks<4>(p, taddr, ch0, t.n, r, c, valid);
                 else
                     for (int j = 0; j < chh; j++) epilogue_chunks<1>(p, taddr, ch0 + j, t.n, r, c, valid);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_accempty + 8 * mt);      // this M-tile's accumulator may be overwritten
+                if (lane == 0) mbar_arrive(bar_accempty + 8 * (4 * buf + mt));      // this accumulator may be overwritten
             }
             // M-tiles this tile did not use still owe their issuer warp an arrival
             for (int mt = t.mt_count; mt < 4; mt++) {
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_accempty + 8 * mt);
+                if (lane == 0) mbar_arrive(bar_accempty + 8 * (4 * buf + mt));
             }
         }
     }
