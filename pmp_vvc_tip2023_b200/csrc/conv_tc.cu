@@ -44,25 +44,25 @@ struct TcGeom {
     uint32_t plane_bytes, group_bytes, act_bytes, stage_bytes, smem_bytes, tmem_cols;
 };
 
-static bool tc_geometry(int cin_pad, int cout_pad, int k, int H, int W, TcGeom &g)
+static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W, TcGeom &g)
 {
-    if (!(k == 1 || k == 3 || k == 5)) return false;
+    if (kh < 1 || kh > 9 || kw < 1 || kw > 5) return false;
     if (cin_pad % 16 || cout_pad % 16 || cin_pad < 16 || cout_pad < 16 || cout_pad > 64) return false;
     if (H < 16 || W < 16 || (W & 1)) return false;
     g.groups = cin_pad / 16;
     if (g.groups > TC_MAX_GROUPS) return false;
     g.coutp = cout_pad;
     g.N1 = 2 * cout_pad;
-    g.P = W + k - 1;
+    g.P = W + kw - 1;
     g.total_mt = (H * g.P + 127) / 128;
     g.stage_bytes = 32u * g.N1;
     for (int mt = (g.total_mt < 4 ? g.total_mt : 4); mt >= 1; mt--) {
-        int maxidx = g.P - 1 + mt * 128 - 1 + (k - 1) * (g.P + 1);
+        int maxidx = g.P - 1 + mt * 128 - 1 + (kh - 1) * g.P + (kw - 1);
         int rbox = maxidx / g.P + 1;
         if (rbox > 256) continue;
         uint32_t plane = (uint32_t)rbox * g.P * 16;
         uint32_t act = plane * 4 * g.groups;
-        if (TC_SMEM_HEADER + act + (uint32_t)(k + 3) * g.stage_bytes > TC_SMEM_MAX) continue;   // ring >= one filter row + 2
+        if (TC_SMEM_HEADER + act + (uint32_t)(kw + 3) * g.stage_bytes > TC_SMEM_MAX) continue;  // ring >= one filter row + 2
         int ns = (int)((TC_SMEM_MAX - TC_SMEM_HEADER - act) / g.stage_bytes);
         if (ns > TC_MAX_STAGES) ns = TC_MAX_STAGES;
         g.MT = mt; g.Rbox = rbox; g.plane_bytes = plane; g.group_bytes = plane * 4; g.act_bytes = act;
@@ -77,15 +77,15 @@ static bool tc_geometry(int cin_pad, int cout_pad, int k, int H, int W, TcGeom &
     return false;
 }
 
-bool tc_supported(int cin_pad, int cout_pad, int ksize, int H, int W)
+bool tc_supported(int cin_pad, int cout_pad, int kh, int kw, int H, int W)
 {
     TcGeom g;
-    return tc_geometry(cin_pad, cout_pad, ksize, H, W, g);
+    return tc_geometry(cin_pad, cout_pad, kh, kw, H, W, g);
 }
 
-size_t tc_packed_elems(int cin_pad, int cout_pad, int ksize)
+size_t tc_packed_elems(int cin_pad, int cout_pad, int kh, int kw)
 {
-    return (size_t)ksize * ksize * (cin_pad / 16) * 2 * (2 * cout_pad) * 8;
+    return (size_t)kh * kw * (cin_pad / 16) * 2 * (2 * cout_pad) * 8;
 }
 
 static inline void host_split(float w, bool bf16, uint16_t &hi, uint16_t &lo)
@@ -101,10 +101,10 @@ static inline void host_split(float w, bool bf16, uint16_t &hi, uint16_t &lo)
     }
 }
 
-// [group][tap][k8 (2)][n (2*cout_pad: hi couts then lo couts)][8 cin] 16-bit; w is the reference's [cout][cin][k][k] fp32
-void pack_tc_weights(const float *w, int cout, int cin, int ksize, int cin_pad, int cout_pad, bool bf16, uint16_t *dst)
+// [group][tap][k8 (2)][n (2*cout_pad: hi couts then lo couts)][8 cin] 16-bit; w is the reference's [cout][cin][kh][kw] fp32
+void pack_tc_weights(const float *w, int cout, int cin, int kh, int kw, int cin_pad, int cout_pad, bool bf16, uint16_t *dst)
 {
-    const int groups = cin_pad / 16, N1 = 2 * cout_pad, taps = ksize * ksize;
+    const int groups = cin_pad / 16, N1 = 2 * cout_pad, taps = kh * kw;
     for (int t = 0; t < taps; t++)
         for (int g = 0; g < groups; g++)
             for (int k8 = 0; k8 < 2; k8++)
@@ -207,8 +207,9 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
 
 struct TcParams {
     const uint16_t *w;
+    const float *bias;
     Act out, res, mul;
-    int H, W, P, k, pad, groups, total_mt, tiles, N1, coutp, nstages, items;
+    int H, W, P, kh, kw, pady, padx, groups, total_mt, tiles, N1, coutp, nstages, items;
     uint32_t plane_bytes, group_bytes, stage_bytes, tmem_cols, idesc1, idesc2;
     int relu;
 };
@@ -298,6 +299,12 @@ __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t tadd
     uint4 *ob = reinterpret_cast<uint4 *>(p.out.p) + (size_t)n * (p.out.Cp >> 2) * plane + pix;
 #pragma unroll
     for (int j = 0; j < CH; j++) {
+        if (p.bias) {       // stems only; padded to Cout_pad on the host
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias) + 2 * (ch0 + j));
+            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias) + 2 * (ch0 + j) + 1);
+            v[j][0] += b0.x; v[j][1] += b0.y; v[j][2] += b0.z; v[j][3] += b0.w;
+            v[j][4] += b1.x; v[j][5] += b1.y; v[j][6] += b1.z; v[j][7] += b1.w;
+        }
         if (p.res.p) {
             float rv[8];
             unpack_split(rh[j], rl[j], bf, rv);
@@ -343,7 +350,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
     uint8_t *ring = act + (size_t)p.groups * p.group_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int taps = p.k * p.k;
+    const int taps = p.kh * p.kw;
 
     if (threadIdx.x == 0) {
         for (int g = 0; g < p.groups; g++) { mbar_init(bar_afull + 8 * g, 1); mbar_init(bar_aempty + 8 * g, TC_MMA_WARPS); }
@@ -389,8 +396,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
                 for (int g = 0; g < p.groups; g++) {
                     mbar_wait(bar_aempty + 8 * g, (idx & 1u) ^ 1u);
                     mbar_expect_tx(bar_afull + 8 * g, p.group_bytes);
-                    tma_load_4d(smem_u32(act + (size_t)g * p.group_bytes), &tmap, bar_afull + 8 * g, -2 * p.pad,
-                                t.row0 - p.pad, g * 4, t.n);
+                    tma_load_4d(smem_u32(act + (size_t)g * p.group_bytes), &tmap, bar_afull + 8 * g, -2 * p.padx,
+                                t.row0 - p.pady, g * 4, t.n);
                 }
             }
         }
@@ -405,7 +412,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
         const uint32_t act16 = (smem_u32(act) >> 4) + (uint32_t)m * 128u, ring16 = smem_u32(ring) >> 4;
         const uint32_t group16 = p.group_bytes >> 4, stage16 = p.stage_bytes >> 4, lo16 = (2u * p.plane_bytes) >> 4;
         const uint32_t idesc = p.idesc2, wlo16 = (uint32_t)p.coutp;                              // w_lo rows follow w_hi rows
-        const int K = p.k, P = p.P, NS = p.nstages, G = p.groups;
+        const int KH = p.kh, K = p.kw, P = p.P, NS = p.nstages, G = p.groups;
         uint32_t s = 0, ph = 0, idx = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, idx++) {
             const TileGeom t = tile_geom(p, item);
@@ -418,7 +425,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
             for (int g = 0; g < G; g++) {
                 mbar_wait(bar_afull + 8 * g, idx & 1u);
                 const uint32_t ag = act16 + (uint32_t)g * group16 + (uint32_t)t.qoff;
-                for (int ky = 0; ky < K; ky++) {
+                for (int ky = 0; ky < KH; ky++) {
                     // one filter row = K weight slabs: probe all their barriers back to back, then spin on stragglers
                     uint32_t sj[5], pj[5];
                     bool ok[5];
@@ -552,10 +559,10 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
 {
     if (B <= 0) return PMP_OK;
     TcGeom g;
-    const int H = a.in.H, W = a.in.W;
-    if (a.in.fmt != FMT_SPLIT || a.out.fmt != FMT_SPLIT || !tc_geometry(a.cin_pad, a.cout_pad, a.ksize, H, W, g) ||
-        a.in.Cp != a.cin_pad || a.out.Cp != a.cout_pad || a.pool != 1 || a.in2.p) {
-        set_error("conv_tc: unsupported configuration cin %d cout %d k %d %dx%d", a.cin_pad, a.cout_pad, a.ksize, H, W);
+    const int H = a.Ho ? a.Ho : a.in.H, W = a.in.W, Hin = a.in.H;
+    if (a.in.fmt != FMT_SPLIT || a.out.fmt != FMT_SPLIT || !tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g) ||
+        a.in.Cp != a.cin_pad || a.out.Cp != a.cout_pad || a.pool != 1 || a.in2.p || a.out.H != H || a.out.W != W) {
+        set_error("conv_tc: unsupported configuration cin %d cout %d k %dx%d %dx%d", a.cin_pad, a.cout_pad, a.kh, a.kw, H, W);
         return PMP_ERR_UNSUPPORTED;
     }
     EncodeTiledFn enc = nullptr;
@@ -566,8 +573,8 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     // 8-byte elements: a pixel's 8-channel unit is two elements, so the inner box dimension is a whole P-pixel row
     // (P*16 contiguous bytes) instead of one 16-byte unit (a 16-byte inner dimension makes every request pull a 32-byte
     // sector: measured 2x L2->SM traffic)
-    cuuint64_t gdim[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, planes, (cuuint64_t)B};
-    cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, planes * H * W * 16};
+    cuuint64_t gdim[4] = {(cuuint64_t)W * 2, (cuuint64_t)Hin, planes, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)Hin * W * 16, planes * Hin * W * 16};
     cuuint32_t box[4] = {(cuuint32_t)g.P * 2, (cuuint32_t)g.Rbox, 4, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, a.in.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -578,8 +585,8 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         return PMP_ERR_CUDA;
     }
     TcParams p;
-    p.w = a.w; p.out = a.out; p.res = a.res; p.mul = a.mul;
-    p.H = H; p.W = W; p.P = g.P; p.k = a.ksize; p.pad = a.ksize / 2; p.groups = g.groups;
+    p.w = a.w; p.bias = a.bias; p.out = a.out; p.res = a.res; p.mul = a.mul;
+    p.H = H; p.W = W; p.P = g.P; p.kh = a.kh; p.kw = a.kw; p.pady = a.pad_t; p.padx = a.pad_l; p.groups = g.groups;
     p.total_mt = g.total_mt; p.tiles = g.tiles; p.N1 = g.N1; p.coutp = g.coutp; p.nstages = g.nstages;
     p.items = g.tiles * B;
     p.plane_bytes = g.plane_bytes; p.group_bytes = g.group_bytes; p.stage_bytes = g.stage_bytes; p.tmem_cols = g.tmem_cols;
@@ -594,7 +601,7 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         attr_set = true;
     }
     dim3 grid(p.items < h->num_sms ? p.items : h->num_sms);
-    const double flops = 2.0 * B * H * W * (double)a.out.C * a.in.C * a.ksize * a.ksize;
+    const double flops = a.flops_override > 0 ? a.flops_override * B : 2.0 * B * H * W * (double)a.out.C * a.in.C * a.kh * a.kw;
     ProfScope ps(h, PROF_CONV_TC, s, flops, 0);
     conv_tc_kernel<<<grid, TC_THREADS, g.smem_bytes, s>>>(tmap, p);
     h->launches++;
@@ -639,6 +646,41 @@ int pool2_split(Handle *h, const Act &in, const Act &out, const Act &mul, int B,
     int grid = (int)((total + 255) / 256);
     ProfScope ps(h, PROF_ELEMWISE, s, 0, (double)total * 32 * 5);
     pool2_split_kernel<<<grid, 256, 0, s>>>(in, out, mul, B);
+    h->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
+// First-layer input with the kx taps unrolled into channels (see kernels.cuh).  One thread per (n, chunk, y, x).
+__global__ void stem_unroll_kernel(Act x, const float *__restrict__ qt, int up, int ov, int kw, Act out, int B)
+{
+    const int S0 = x.H, W = out.W, H = out.H, nch = out.Cp >> 3, cx = x.C;
+    size_t total = (size_t)B * nch * H * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % W), yy = (int)((i / W) % H), ch = (int)((i / ((size_t)W * H)) % nch);
+        const int n = (int)(i / ((size_t)W * H * nch));
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int cu = ch * 8 + e, c = cu / kw, j = cu - c * kw, sx = xx + j;
+            float val = 0.f;
+            if (sx < S0) {
+                if (c < cx) val = load_elem(x, n, c, yy, sx);
+                else if (c == cx && qt && yy >= ov && sx >= ov) val = qt[(size_t)n * 64 + ((yy - ov) / up) * 8 + (sx - ov) / up];
+            }
+            v[e] = val;
+        }
+        store_chunk_split(out, n, ch, yy, xx, v);
+    }
+}
+
+int stem_unroll(Handle *h, const Act &x, const float *qt, int up, int ov, int kw, const Act &out, int B, cudaStream_t s)
+{
+    size_t total = (size_t)B * (out.Cp >> 3) * out.H * out.W;
+    if (!total) return PMP_OK;
+    int grid = (int)((total + 255) / 256);
+    ProfScope ps(h, PROF_ELEMWISE, s, 0, (double)total * 32 + (double)B * x.C * x.H * x.W);
+    stem_unroll_kernel<<<grid, 256, 0, s>>>(x, qt, up, ov, kw, out, B);
     h->launches++;
     PMP_CUDA(cudaGetLastError());
     return PMP_OK;
@@ -703,7 +745,7 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     const int B = batch, H = hw, W = hw;
     const bool bf = (flags & 8) != 0;
     const int cinp = pad16(cin), coutp = pad16(cout);
-    if (!tc_supported(cinp, coutp, ksize, H, W)) {
+    if (!tc_supported(cinp, coutp, ksize, ksize, H, W)) {
         set_error("selftest: configuration not supported by the TC engine");
         return PMP_ERR_UNSUPPORTED;
     }
@@ -733,8 +775,8 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     for (int o = 0; o < cout; o++)
         for (int c = 0; c < cin; c++)
             for (int t = 0; t < taps; t++) ps[((size_t)c * taps + t) * coutw + o] = hw_[((size_t)o * cin + c) * taps + t];
-    std::vector<uint16_t> pk(tc_packed_elems(cinp, coutp, ksize));
-    pack_tc_weights(hw_.data(), cout, cin, ksize, cinp, coutp, bf, pk.data());
+    std::vector<uint16_t> pk(tc_packed_elems(cinp, coutp, ksize, ksize));
+    pack_tc_weights(hw_.data(), cout, cin, ksize, ksize, cinp, coutp, bf, pk.data());
     if (d_wsimt.alloc(ps.size() * 4) || d_wtc.alloc(pk.size() * 2)) return PMP_ERR_CUDA;
     PMP_CUDA(cudaMemcpy(d_wsimt.p, ps.data(), ps.size() * 4, cudaMemcpyHostToDevice));
     PMP_CUDA(cudaMemcpy(d_wtc.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
@@ -770,7 +812,7 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     ta.in = in; ta.out = out;
     if (flags & 2) ta.res = res;
     if (flags & 4) ta.mul = mul;
-    ta.w = (const uint16_t *)d_wtc.p; ta.cin_pad = cinp; ta.cout_pad = coutp; ta.ksize = ksize; ta.relu = flags & 1; ta.pool = 1;
+    ta.w = (const uint16_t *)d_wtc.p; ta.cin_pad = cinp; ta.cout_pad = coutp; ta.kh = ta.kw = ksize; ta.pad_t = ta.pad_l = ksize / 2; ta.relu = flags & 1; ta.pool = 1;
     rc = conv_tc(h, ta, B, s);          // warm-up (also first-launch overheads)
     cudaEventRecord(e2, s);
     if (!rc) rc = conv_tc(h, ta, B, s);

@@ -83,6 +83,54 @@ static int dev_upload(WeightSet &ws, const std::vector<T> &host, T **dev)
     return PMP_OK;
 }
 
+// Tensor-core form of the first-layer convs: the kx taps are unrolled into input channels (cu = c*kw + j, see
+// stem_unroll in kernels.cuh), which turns the kh x kw valid conv on 1..4 channels into a kh x 1 conv on cin*kw channels.
+// The three MSBD stems (Model_QBD.py:108-110: kb x kb -> 16, ks x kb -> 8, kb x ks -> 8 channels, concatenated :135)
+// become ONE 32-output conv by embedding the smaller kernels top/left-aligned in kb x kb (their zero pads are the
+// corresponding sides, :104-106).  Stored as ConvW "stem_tc": cin = cin*kb, kh = kb, kw = 1, bias padded to cout_pad.
+static int build_stem_tc(WeightSet &ws, int net, const std::vector<ParamSpec> &spec, const float *const *tensors)
+{
+    auto find = [&](const char *name) -> int {
+        for (size_t i = 0; i < spec.size(); i++)
+            if (spec[i].name == name) return (int)i;
+        return -1;
+    };
+    const bool q = (net == PMP_NET_LUMA_Q || net == PMP_NET_CHROMA_Q);
+    struct Part { int iw, ib, co_off; };
+    std::vector<Part> parts;
+    if (q) parts.push_back({find("conv_q1.weight"), find("conv_q1.bias"), 0});
+    else {
+        parts.push_back({find("conv_b1_1.weight"), find("conv_b1_1.bias"), 0});
+        parts.push_back({find("conv_b1_2.weight"), find("conv_b1_2.bias"), 16});
+        parts.push_back({find("conv_b1_3.weight"), find("conv_b1_3.bias"), 24});
+    }
+    const int cin = spec[parts[0].iw].d[1], kb = spec[parts[0].iw].d[2];
+    const int cu = cin * kb, cout = 32;
+    std::vector<float> wm((size_t)cout * cu * kb, 0.f), bias(pad16(cout), 0.f);      // [co][cu][ky]  (kw = 1)
+    for (const Part &pt : parts) {
+        if (pt.iw < 0 || pt.ib < 0) { set_error("stem parameters missing"); return PMP_ERR_STATE; }
+        const int co = spec[pt.iw].d[0], kh = spec[pt.iw].d[2], kw = spec[pt.iw].d[3];
+        const float *w = tensors[pt.iw];
+        for (int o = 0; o < co; o++) {
+            bias[pt.co_off + o] = tensors[pt.ib][o];
+            for (int c = 0; c < cin; c++)
+                for (int ky = 0; ky < kh; ky++)
+                    for (int j = 0; j < kw; j++)
+                        wm[((size_t)(pt.co_off + o) * cu + (c * kb + j)) * kb + ky] = w[(((size_t)o * cin + c) * kh + ky) * kw + j];
+        }
+    }
+    ConvW &cw = ws.convs["stem_tc"];
+    cw.cout = cout; cw.cin = cu; cw.kh = kb; cw.kw = 1; cw.cin_pad = pad16(cu); cw.cout_pad = pad16(cout);
+    int rc = dev_upload(ws, bias, &cw.bias);
+    if (rc) return rc;
+    std::vector<uint16_t> pk(tc_packed_elems(cw.cin_pad, cw.cout_pad, kb, 1));
+    pack_tc_weights(wm.data(), cout, cu, kb, 1, cw.cin_pad, cw.cout_pad, false, pk.data());
+    rc = dev_upload(ws, pk, &cw.w_tc_f16);
+    if (rc) return rc;
+    pack_tc_weights(wm.data(), cout, cu, kb, 1, cw.cin_pad, cw.cout_pad, true, pk.data());
+    return dev_upload(ws, pk, &cw.w_tc_bf16);
+}
+
 int weights_create(Handle *h, int net, const float *const *tensors, const int64_t *numel, int n, int *wset)
 {
     std::vector<ParamSpec> spec = param_spec(net);
@@ -127,15 +175,16 @@ int weights_create(Handle *h, int net, const float *const *tensors, const int64_
         if (rc) break;
         // TC operand images (both 16-bit formats) for the square kernels the tcgen05 engine covers
         if (kh == kw && (kh == 1 || kh == 3 || kh == 5) && ci >= 3) {
-            std::vector<uint16_t> pk(tc_packed_elems(cw.cin_pad, cw.cout_pad, kh));
+            std::vector<uint16_t> pk(tc_packed_elems(cw.cin_pad, cw.cout_pad, kh, kw));
             if (pk.empty()) continue;
-            pack_tc_weights(tensors[i], co, ci, kh, cw.cin_pad, cw.cout_pad, false, pk.data());
+            pack_tc_weights(tensors[i], co, ci, kh, kw, cw.cin_pad, cw.cout_pad, false, pk.data());
             rc = dev_upload(ws, pk, &cw.w_tc_f16);
             if (rc) break;
-            pack_tc_weights(tensors[i], co, ci, kh, cw.cin_pad, cw.cout_pad, true, pk.data());
+            pack_tc_weights(tensors[i], co, ci, kh, kw, cw.cin_pad, cw.cout_pad, true, pk.data());
             rc = dev_upload(ws, pk, &cw.w_tc_bf16);
         }
     }
+    if (rc == PMP_OK) rc = build_stem_tc(ws, net, spec, tensors);
     if (rc != PMP_OK) {
         weights_destroy(h, id);
         return rc;
@@ -215,12 +264,12 @@ struct Net {
         const bool use_tc = tc && same && in.fmt == FMT_SPLIT && out.fmt == FMT_SPLIT && o.out_c_off == 0 && !o.add0 &&
                             !w->bias && out.C == w->cout && in.C == w->cin && (!o.res.p || o.res.fmt == FMT_SPLIT) &&
                             (!o.mul.p || o.mul.fmt == FMT_SPLIT) && (in.bf16 ? w->w_tc_bf16 : w->w_tc_f16) &&
-                            tc_supported(w->cin_pad, w->cout_pad, w->kh, in.H, in.W);
+                            tc_supported(w->cin_pad, w->cout_pad, w->kh, w->kw, in.H, in.W);
         if (use_tc) {
             TcConvArgs a;
             a.in = in; a.res = o.res; a.mul = o.mul;
             a.w = in.bf16 ? w->w_tc_bf16 : w->w_tc_f16;
-            a.cin_pad = w->cin_pad; a.cout_pad = w->cout_pad; a.ksize = w->kh;
+            a.cin_pad = w->cin_pad; a.cout_pad = w->cout_pad; a.kh = w->kh; a.kw = w->kw; a.pad_t = pad_t; a.pad_l = pad_l;
             a.relu = o.relu; a.pool = 1;
             if (o.pool == 2) {
                 // v1: un-pooled conv into a temporary, then a pooling pass (mul applies after pooling)
@@ -246,6 +295,29 @@ struct Net {
         a.relu = o.relu; a.pool = o.pool; a.out_c_off = o.out_c_off;
         a.add0 = o.add0; a.add0_bstride = o.add0_bstride;
         rc = conv_simt(h, a, w->kh, w->kw, B, s);
+    }
+
+    // first-layer conv(s) on the tensor cores: unroll kx into channels, then one kh x 1 conv with bias + ReLU.
+    // Returns false when the TC path is not usable (engine SIMT): the caller runs the SIMT stems instead.
+    bool stem_tc(const Act &x, const float *qt, int up, int ov, const Act &out, double flops_per_image)
+    {
+        if (!tc || rc) return false;
+        const ConvW *w = weights("stem_tc");
+        if (!w) return false;
+        const uint16_t *wp = (h->tc_dtype == PMP_TC_BF16) ? w->w_tc_bf16 : w->w_tc_f16;
+        if (!wp || !tc_supported(w->cin_pad, w->cout_pad, w->kh, 1, out.H, out.W)) return false;
+        const size_t mark = off;
+        Act u = alloc(w->cin, x.H, out.W, FMT_SPLIT);
+        if (!dry) {
+            rc = stem_unroll(h, x, qt, up, ov, w->kh, u, B, s);
+            TcConvArgs a;
+            a.in = u; a.out = out; a.w = wp; a.bias = w->bias;
+            a.cin_pad = w->cin_pad; a.cout_pad = w->cout_pad; a.kh = w->kh; a.kw = 1; a.pad_t = 0; a.pad_l = 0;
+            a.Ho = out.H; a.relu = 1; a.pool = 1; a.flops_override = flops_per_image;
+            if (!rc) rc = conv_tc(h, a, B, s);
+        }
+        off = mark;
+        return true;
     }
 
     // ResidualBlock (Model_QBD.py:23-44) into `out`; scratch activations are released on return
@@ -308,9 +380,12 @@ static void run_q(Net &n, bool luma, const void *blocks, int in_dtype, float *qt
     const int S0 = luma ? 68 : 34, S1 = luma ? 64 : 32;
     Act x = input_act(blocks, in_dtype, luma ? 1 : 3, S0);
     Act x2 = n.act(32, S1, S1);
-    ConvOpts c1;
-    c1.relu = 1; c1.pad_t = 0; c1.pad_l = 0; c1.Ho = S1; c1.Wo = S1;       // padding_rb + valid conv (:79-80)
-    n.conv("conv_q1", x, x2, c1);
+    const int k1 = luma ? 9 : 5;
+    if (!n.stem_tc(x, nullptr, 1, 0, x2, 2.0 * S1 * S1 * 32.0 * x.C * k1 * k1)) {
+        ConvOpts c1;
+        c1.relu = 1; c1.pad_t = 0; c1.pad_l = 0; c1.Ho = S1; c1.Wo = S1;   // padding_rb + valid conv (:79-80)
+        n.conv("conv_q1", x, x2, c1);
+    }
     const int S3 = 32;
     Act x3 = n.act(64, S3, S3);
     n.resblock("resblock_q1", x2, 64, x3, luma ? 2 : 1, Act());           // :81 pools, :179 does not
@@ -344,14 +419,18 @@ static void run_msbd(Net &n, bool luma, const void *blocks, int in_dtype, const 
     const int S0 = luma ? 68 : 34, S1 = luma ? 64 : 32, ov = luma ? 4 : 2, up = luma ? 8 : 4;
     const int cx = luma ? 1 : 3;
     Act x = input_act(blocks, in_dtype, cx, S0);
-    Act x2 = n.alloc(cx + 1, S0, S0, FMT_F32);                            // cat[x, pad_lu(up(qt))] (:130-131)
-    if (!n.dry && !n.rc) n.rc = stem_input(n.h, x, qt, up, ov, x2, n.B, n.s);
     Act x3 = n.act(32, S1, S1);
-    ConvOpts st;
-    st.relu = 1; st.pad_t = 0; st.pad_l = 0; st.Ho = S1; st.Wo = S1;      // asymmetric zero pads == OOB reads (:132-134)
-    st.out_c_off = 0;  n.conv("conv_b1_1", x2, x3, st);
-    st.out_c_off = 16; n.conv("conv_b1_2", x2, x3, st);
-    st.out_c_off = 24; n.conv("conv_b1_3", x2, x3, st);
+    const int kb = luma ? 9 : 5, ks = luma ? 5 : 3;
+    const double stem_flops = 2.0 * S1 * S1 * (cx + 1) * (16.0 * kb * kb + 16.0 * kb * ks);
+    if (!n.stem_tc(x, qt, up, ov, x3, stem_flops)) {
+        Act x2 = n.alloc(cx + 1, S0, S0, FMT_F32);                        // cat[x, pad_lu(up(qt))] (:130-131)
+        if (!n.dry && !n.rc) n.rc = stem_input(n.h, x, qt, up, ov, x2, n.B, n.s);
+        ConvOpts st;
+        st.relu = 1; st.pad_t = 0; st.pad_l = 0; st.Ho = S1; st.Wo = S1;  // asymmetric zero pads == OOB reads (:132-134)
+        st.out_c_off = 0;  n.conv("conv_b1_1", x2, x3, st);
+        st.out_c_off = 16; n.conv("conv_b1_2", x2, x3, st);
+        st.out_c_off = 24; n.conv("conv_b1_3", x2, x3, st);
+    }
     const int S4 = 32;
     Act x4 = n.act(64, S4, S4);
     n.trunk("trunk_M1", x3, {64, 64, 64, 64, 64, 64}, x4, luma ? 2 : 1, Act());      // :136 / :234
