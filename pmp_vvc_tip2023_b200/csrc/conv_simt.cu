@@ -213,44 +213,62 @@ int stem_input(Handle *h, const Act &x, const float *qt, int up, int ov, const A
 }
 
 // x6 = cat[x5, up2(pool2 x5), up4(pool4 x5), up8(pool8 x5)]  (Model_QBD.py:84-87): [B,32,16,16] -> [B,128,16,16]
-// one thread per (n, group g, 8-channel chunk, y, x)
-__global__ void pyramid_kernel(Act in, Act out, int B)
+// One CTA per (8-channel chunk, image), one thread per pixel of the 16x16 map; the 2x2 / 4x4 / 8x8 block maxima are
+// built hierarchically in shared memory (each level reads 4 entries of the previous one).
+__global__ void __launch_bounds__(256) pyramid_kernel(Act in, Act out)
 {
-    const int H = in.H, W = in.W, nchunk = in.C >> 3;
-    size_t total = (size_t)B * 4 * nchunk * H * W;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        int x = (int)(i % W), y = (int)((i / W) % H), ch = (int)((i / ((size_t)W * H)) % nchunk);
-        int g = (int)((i / ((size_t)W * H * nchunk)) % 4), n = (int)(i / ((size_t)W * H * nchunk * 4));
-        int sft = g, y0 = (y >> sft) << sft, x0 = (x >> sft) << sft, span = 1 << sft;
-        float m[8];
+    __shared__ float lvl[3][8][256];
+    const int ch = blockIdx.x, n = blockIdx.y, t = threadIdx.x, y = t >> 4, x = t & 15;
+    float v[8];
+    if (in.fmt == FMT_SPLIT) load_chunk_split(in, n, ch, y, x, v);
+    else {
 #pragma unroll
-        for (int e = 0; e < 8; e++) m[e] = -3.0e38f;
-        for (int dy = 0; dy < span; dy++)
-            for (int dx = 0; dx < span; dx++) {
-                float v[8];
-                if (in.fmt == FMT_SPLIT) load_chunk_split(in, n, ch, y0 + dy, x0 + dx, v);
-                else {
-#pragma unroll
-                    for (int e = 0; e < 8; e++) v[e] = load_elem(in, n, ch * 8 + e, y0 + dy, x0 + dx);
-                }
-#pragma unroll
-                for (int e = 0; e < 8; e++) m[e] = fmaxf(m[e], v[e]);
-            }
-        int oc = g * in.C + ch * 8;
+        for (int e = 0; e < 8; e++) v[e] = load_elem(in, n, ch * 8 + e, y, x);
+    }
+    auto emit = [&](int g, const float m[8]) {
+        const int oc = g * in.C + ch * 8;
         if (out.fmt == FMT_SPLIT) store_chunk_split(out, n, oc >> 3, y, x, m);
         else {
 #pragma unroll
             for (int e = 0; e < 8; e++) store_elem_f32(out, n, oc + e, y, x, m[e]);
+        }
+    };
+    emit(0, v);
+#pragma unroll
+    for (int e = 0; e < 8; e++) lvl[0][e][t] = v[e];
+    __syncthreads();
+#pragma unroll
+    for (int g = 1; g <= 3; g++) {
+        const int half = 1 << (g - 1), y0 = (y >> g) << g, x0 = (x >> g) << g;     // children at stride `half`
+        const float (*src)[256] = lvl[g - 1];
+        float m[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const float a = src[e][y0 * 16 + x0], b = src[e][y0 * 16 + x0 + half];
+            const float c = src[e][(y0 + half) * 16 + x0], d = src[e][(y0 + half) * 16 + x0 + half];
+            m[e] = fmaxf(fmaxf(a, b), fmaxf(c, d));
+        }
+        emit(g, m);
+        if (g < 3) {
+            // level g maxima live at the block origins of lvl[g]; every thread writes its own block's value (same
+            // value from all threads of a block: benign)
+#pragma unroll
+            for (int e = 0; e < 8; e++) lvl[g][e][y0 * 16 + x0] = m[e];
+            __syncthreads();
         }
     }
 }
 
 int pyramid(Handle *h, const Act &in, const Act &out, int B, cudaStream_t s)
 {
-    size_t total = (size_t)B * 4 * (in.C >> 3) * in.H * in.W;
-    int grid = (int)((total + 255) / 256);
-    ProfScope ps(h, PROF_ELEMWISE, s, 0, (double)total * 8 * 4 * 2);
-    pyramid_kernel<<<grid, 256, 0, s>>>(in, out, B);
+    if (B <= 0) return PMP_OK;
+    if (in.H != 16 || in.W != 16 || (in.C & 7)) {
+        set_error("pyramid: expected a [B,8k,16,16] input");
+        return PMP_ERR_UNSUPPORTED;
+    }
+    dim3 grid(in.C >> 3, B);
+    ProfScope ps(h, PROF_ELEMWISE, s, 0, (double)B * in.C * 256 * 4 * 5);
+    pyramid_kernel<<<grid, 256, 0, s>>>(in, out);
     h->launches++;
     PMP_CUDA(cudaGetLastError());
     return PMP_OK;

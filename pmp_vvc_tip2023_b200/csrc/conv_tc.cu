@@ -40,9 +40,16 @@ constexpr uint32_t TC_SMEM_HEADER = 1024;
 constexpr uint32_t TC_SMEM_MAX = 232448;          // 227 KB dynamic shared memory per CTA
 
 struct TcGeom {
-    int P, MT, total_mt, tiles, Rbox, groups, N1, coutp, nstages;
+    int P, MT, total_mt, tiles, Rbox, groups, N1, coutp, nstages, stacked, pairbuf;
     uint32_t plane_bytes, group_bytes, act_bytes, stage_bytes, smem_bytes, tmem_cols;
 };
+
+// Accumulator schemes (both double-buffer the accumulators so the epilogue overlaps the next tile's MMAs):
+//   unstacked : 3 MMAs (N = Cout) per tap; 4 M-tiles x 2 buffers x Cout columns.       Default for Cout = 64.
+//   stacked   : 2 MMAs (N = 2*Cout, Cout) per tap; fewer instructions and operand reads, 2*Cout columns per M-tile:
+//               4 M-tiles x 2 buffers when 16*Cout <= 512 (default for Cout <= 32, which are issue-bound), else
+//               2 M-tiles x 2 buffers with issuer pairs owning alternate tiles ("pairbuf"; measured slower, kept as an option).
+static int g_tc_scheme = -1;     // -1 auto, 0 unstacked, 1 stacked
 
 static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W, TcGeom &g)
 {
@@ -56,7 +63,15 @@ static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W,
     g.P = W + kw - 1;
     g.total_mt = (H * g.P + 127) / 128;
     g.stage_bytes = 32u * g.N1;
-    for (int mt = (g.total_mt < 4 ? g.total_mt : 4); mt >= 1; mt--) {
+    static const int env_scheme = [] {
+        const char *e = getenv("PMP_TC_SCHEME");       // tuning/A-B knob: 0 unstacked, 1 stacked
+        return e ? atoi(e) : -1;
+    }();
+    const int scheme = g_tc_scheme < 0 ? env_scheme : g_tc_scheme;
+    g.stacked = scheme == 1 || (scheme < 0 && cout_pad <= 32);
+    g.pairbuf = g.stacked && 16 * cout_pad > 512;
+    const int mt_max = g.pairbuf ? 2 : 4;
+    for (int mt = (g.total_mt < mt_max ? g.total_mt : mt_max); mt >= 1; mt--) {
         int maxidx = g.P - 1 + mt * 128 - 1 + (kh - 1) * g.P + (kw - 1);
         int rbox = maxidx / g.P + 1;
         if (rbox > 256) continue;
@@ -69,7 +84,7 @@ static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W,
         g.nstages = ns;
         g.smem_bytes = TC_SMEM_HEADER + act + ns * g.stage_bytes;
         g.tiles = (g.total_mt + mt - 1) / mt;
-        uint32_t cols = 8u * g.coutp, pc = 32;     // 2 accumulator buffers x 4 M-tiles x Cout columns
+        uint32_t cols = (g.stacked && !g.pairbuf ? 16u : 8u) * g.coutp, pc = 32;
         while (pc < cols) pc <<= 1;
         g.tmem_cols = pc;
         return pc <= 512;
@@ -211,7 +226,7 @@ struct TcParams {
     Act out, res, mul;
     int H, W, P, kh, kw, pady, padx, groups, total_mt, tiles, N1, coutp, nstages, items;
     uint32_t plane_bytes, group_bytes, stage_bytes, tmem_cols, idesc1, idesc2;
-    int relu;
+    int relu, stacked, pairbuf;
 };
 
 struct TileGeom { int n, mt_count, q0, row0, qoff; };
@@ -290,9 +305,17 @@ __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t tadd
     for (int j = 0; j < CH; j++) {         // per chunk: small transient register footprint (TMEM latency is short)
         uint32_t a[8];
         tmem_ld8(taddr + 8 * (ch0 + j), a);
-        tmem_wait_ld();
+        if (p.stacked) {        // columns [Cout, 2*Cout) hold a_hi * w_lo
+            uint32_t b[8];
+            tmem_ld8(taddr + p.coutp + 8 * (ch0 + j), b);
+            tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 8; e++) v[j][e] = __uint_as_float(a[e]);
+            for (int e = 0; e < 8; e++) v[j][e] = __uint_as_float(a[e]) + __uint_as_float(b[e]);
+        } else {
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[j][e] = __uint_as_float(a[e]);
+        }
     }
     if (!valid) return;
     const bool bf = p.out.bf16 != 0;
@@ -355,8 +378,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
     if (threadIdx.x == 0) {
         for (int g = 0; g < p.groups; g++) { mbar_init(bar_afull + 8 * g, 1); mbar_init(bar_aempty + 8 * g, TC_MMA_WARPS); }
         for (int s = 0; s < p.nstages; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, TC_MMA_WARPS); }
-        mbar_init(bar_acc, TC_MMA_WARPS);
-        mbar_init(bar_acc + 8, TC_MMA_WARPS);
+        mbar_init(bar_acc, p.pairbuf ? 2 : TC_MMA_WARPS);
+        mbar_init(bar_acc + 8, p.pairbuf ? 2 : TC_MMA_WARPS);
         for (int m = 0; m < 8; m++) mbar_init(bar_accempty + 8 * m, TC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -409,22 +432,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
         const uint64_t desc_c = ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);             // SBO 128, version 1
         const uint64_t adesc_c = desc_c | ((uint64_t)(p.plane_bytes >> 4) << 16);                // LBO = plane stride
         const uint64_t bdesc_c = desc_c | ((uint64_t)(((uint32_t)p.N1 * 16u) >> 4) << 16);       // LBO = N1 rows
-        const uint32_t act16 = (smem_u32(act) >> 4) + (uint32_t)m * 128u, ring16 = smem_u32(ring) >> 4;
+        const uint32_t act16 = smem_u32(act) >> 4, ring16 = smem_u32(ring) >> 4;
         const uint32_t group16 = p.group_bytes >> 4, stage16 = p.stage_bytes >> 4, lo16 = (2u * p.plane_bytes) >> 4;
-        const uint32_t idesc = p.idesc2, wlo16 = (uint32_t)p.coutp;                              // w_lo rows follow w_hi rows
+        const uint32_t idesc = p.idesc2, idesc_st = p.idesc1, wlo16 = (uint32_t)p.coutp;        // w_lo rows follow w_hi rows
         const int KH = p.kh, K = p.kw, P = p.P, NS = p.nstages, G = p.groups;
         uint32_t s = 0, ph = 0, idx = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, idx++) {
             const TileGeom t = tile_geom(p, item);
             const uint32_t buf = idx & 1u;                      // tiles alternate between the two accumulator buffers
-            const bool mine = m < t.mt_count;
-            const uint32_t d_tmem = tmem_base + (buf * 4u + (uint32_t)m) * (uint32_t)p.coutp;
-            mbar_wait(bar_accempty + 8 * (buf * 4 + m), ((idx >> 1) & 1u) ^ 1u);    // epilogue drained it (tile idx-2)
-            tc_fence_after();
+            // default : issuer m owns M-tile m of every tile (accumulator buf*4+m, `accw` columns wide).
+            // pairbuf : issuer m owns M-tile m&1 of the tiles whose buffer is m>>1 (accumulator m); the other two
+            //           issuers only walk the barriers (parity waits must observe every phase).
+            const bool owner = !p.pairbuf || (uint32_t)(m >> 1) == buf;
+            const int mym = p.pairbuf ? (m & 1) : m;
+            const bool mine = owner && mym < t.mt_count;
+            const uint32_t accidx = p.pairbuf ? (uint32_t)m : buf * 4u + (uint32_t)m;
+            const uint32_t d_tmem = tmem_base + accidx * (uint32_t)(p.stacked ? p.N1 : p.coutp);
+            if (owner) {
+                mbar_wait(bar_accempty + 8 * accidx, ((idx >> 1) & 1u) ^ 1u);   // epilogue drained it (tile idx-2)
+                tc_fence_after();
+            }
+            const uint32_t am16 = (uint32_t)mym * 128u;
             uint32_t acc = 0;
             for (int g = 0; g < G; g++) {
                 mbar_wait(bar_afull + 8 * g, idx & 1u);
-                const uint32_t ag = act16 + (uint32_t)g * group16 + (uint32_t)t.qoff;
+                const uint32_t ag = act16 + am16 + (uint32_t)g * group16 + (uint32_t)t.qoff;
                 for (int ky = 0; ky < KH; ky++) {
                     // one filter row = K weight slabs: probe all their barriers back to back, then spin on stragglers
                     uint32_t sj[5], pj[5];
@@ -453,9 +485,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
                                 if (j < K) {
                                     const uint64_t ad = ad0 + (uint64_t)j;
                                     const uint64_t bd = bdesc_c | (uint64_t)(ring16 + sj[j] * stage16);
-                                    umma_f16(d_tmem, ad, bd, idesc, acc);                       // a_hi * w_hi
-                                    umma_f16(d_tmem, ad, bd + (uint64_t)wlo16, idesc, 1u);      // a_hi * w_lo
-                                    umma_f16(d_tmem, ad + (uint64_t)lo16, bd, idesc, 1u);       // a_lo * w_hi
+                                    if (p.stacked) {
+                                        umma_f16(d_tmem, ad, bd, idesc_st, acc);                    // a_hi * [w_hi | w_lo]
+                                        umma_f16(d_tmem, ad + (uint64_t)lo16, bd, idesc, 1u);       // a_lo * w_hi
+                                    } else {
+                                        umma_f16(d_tmem, ad, bd, idesc, acc);                       // a_hi * w_hi
+                                        umma_f16(d_tmem, ad, bd + (uint64_t)wlo16, idesc, 1u);      // a_hi * w_lo
+                                        umma_f16(d_tmem, ad + (uint64_t)lo16, bd, idesc, 1u);       // a_lo * w_hi
+                                    }
                                     umma_commit(bar_wempty + 8 * sj[j]);                        // slab free when read
                                     acc = 1u;
                                 }
@@ -475,7 +512,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
                 }
                 __syncwarp();
             }
-            if (elect_one_sync()) {                              // accumulators of this tile complete
+            if (owner && elect_one_sync()) {                     // accumulators of this tile complete
                 if (mine) umma_commit(bar_acc + 8 * buf);
                 else mbar_arrive(bar_acc + 8 * buf);
             }
@@ -510,18 +547,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
                 const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
                 const int r = pos / p.P, c = pos - r * p.P;
                 const bool valid = (c < p.W) && (r < p.H);
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (4u * buf + (uint32_t)mt) * (uint32_t)p.coutp;
+                const uint32_t accidx = p.pairbuf ? 2u * buf + (uint32_t)mt : 4u * buf + (uint32_t)mt;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + accidx * (uint32_t)(p.stacked ? p.N1 : p.coutp);
                 if (chh == 4) epilogue_chunks<4>(p, taddr, ch0, t.n, r, c, valid);
                 else
                     for (int j = 0; j < chh; j++) epilogue_chunks<1>(p, taddr, ch0 + j, t.n, r, c, valid);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_accempty + 8 * (4 * buf + mt));      // this accumulator may be overwritten
+                if (lane == 0) mbar_arrive(bar_accempty + 8 * accidx);      // this accumulator may be overwritten
             }
             // M-tiles this tile did not use still owe their issuer warp an arrival
-            for (int mt = t.mt_count; mt < 4; mt++) {
+            for (int mt = t.mt_count; mt < (p.pairbuf ? 2 : 4); mt++) {
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_accempty + 8 * (4 * buf + mt));
+                if (lane == 0) mbar_arrive(bar_accempty + 8 * ((p.pairbuf ? 2 : 4) * buf + mt));
             }
         }
     }
@@ -594,7 +632,7 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     const uint32_t idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 4) << 24);
     p.idesc1 = idesc_base | ((uint32_t)(g.N1 >> 3) << 17);
     p.idesc2 = idesc_base | ((uint32_t)(g.coutp >> 3) << 17);
-    p.relu = a.relu;
+    p.relu = a.relu; p.stacked = g.stacked; p.pairbuf = g.pairbuf;
     static bool attr_set = false;
     if (!attr_set) {
         PMP_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
@@ -651,36 +689,37 @@ int pool2_split(Handle *h, const Act &in, const Act &out, const Act &mul, int B,
     return PMP_OK;
 }
 
-// First-layer input with the kx taps unrolled into channels (see kernels.cuh).  One thread per (n, chunk, y, x).
-__global__ void stem_unroll_kernel(Act x, const float *__restrict__ qt, int up, int ov, int kw, Act out, int B)
+// First-layer input with the kx taps unrolled into channels (see kernels.cuh).  grid = (pixel blocks, chunk, image);
+// the (channel, shift) pair of each of the chunk's 8 outputs is advanced incrementally (no per-element division).
+__global__ void stem_unroll_kernel(Act x, const float *__restrict__ qt, int up, int ov, int kw, Act out)
 {
-    const int S0 = x.H, W = out.W, H = out.H, nch = out.Cp >> 3, cx = x.C;
-    size_t total = (size_t)B * nch * H * W;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int xx = (int)(i % W), yy = (int)((i / W) % H), ch = (int)((i / ((size_t)W * H)) % nch);
-        const int n = (int)(i / ((size_t)W * H * nch));
-        float v[8];
+    const int S0 = x.H, W = out.W, H = out.H, cx = x.C;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= H * W) return;
+    const int yy = pix / W, xx = pix - yy * W, ch = blockIdx.y, n = blockIdx.z;
+    int c = (ch * 8) / kw, j = ch * 8 - c * kw;
+    const float *qrow = (qt && yy >= ov) ? qt + (size_t)n * 64 + ((yy - ov) / up) * 8 : nullptr;
+    float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const int cu = ch * 8 + e, c = cu / kw, j = cu - c * kw, sx = xx + j;
-            float val = 0.f;
-            if (sx < S0) {
-                if (c < cx) val = load_elem(x, n, c, yy, sx);
-                else if (c == cx && qt && yy >= ov && sx >= ov) val = qt[(size_t)n * 64 + ((yy - ov) / up) * 8 + (sx - ov) / up];
-            }
-            v[e] = val;
+    for (int e = 0; e < 8; e++) {
+        const int sx = xx + j;
+        float val = 0.f;
+        if (sx < S0) {
+            if (c < cx) val = load_elem(x, n, c, yy, sx);
+            else if (c == cx && qrow && sx >= ov) val = qrow[(sx - ov) / up];
         }
-        store_chunk_split(out, n, ch, yy, xx, v);
+        v[e] = val;
+        if (++j == kw) { j = 0; c++; }
     }
+    store_chunk_split(out, n, ch, yy, xx, v);
 }
 
 int stem_unroll(Handle *h, const Act &x, const float *qt, int up, int ov, int kw, const Act &out, int B, cudaStream_t s)
 {
-    size_t total = (size_t)B * (out.Cp >> 3) * out.H * out.W;
-    if (!total) return PMP_OK;
-    int grid = (int)((total + 255) / 256);
-    ProfScope ps(h, PROF_ELEMWISE, s, 0, (double)total * 32 + (double)B * x.C * x.H * x.W);
-    stem_unroll_kernel<<<grid, 256, 0, s>>>(x, qt, up, ov, kw, out, B);
+    if (B <= 0) return PMP_OK;
+    dim3 grid((out.H * out.W + 255) / 256, out.Cp >> 3, B);
+    ProfScope ps(h, PROF_ELEMWISE, s, 0, (double)B * (out.Cp >> 3) * out.H * out.W * 32 + (double)B * x.C * x.H * x.W);
+    stem_unroll_kernel<<<grid, 256, 0, s>>>(x, qt, up, ov, kw, out);
     h->launches++;
     PMP_CUDA(cudaGetLastError());
     return PMP_OK;
@@ -813,10 +852,13 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     if (flags & 2) ta.res = res;
     if (flags & 4) ta.mul = mul;
     ta.w = (const uint16_t *)d_wtc.p; ta.cin_pad = cinp; ta.cout_pad = coutp; ta.kh = ta.kw = ksize; ta.pad_t = ta.pad_l = ksize / 2; ta.relu = flags & 1; ta.pool = 1;
+    pmp::g_tc_scheme = ((flags >> 8) & 3) - 1;          // 0: library default, 1: unstacked, 2: stacked
+    if (!tc_supported(cinp, coutp, ksize, ksize, H, W)) { pmp::g_tc_scheme = -1; set_error("selftest: scheme not supported"); return PMP_ERR_UNSUPPORTED; }
     rc = conv_tc(h, ta, B, s);          // warm-up (also first-launch overheads)
     cudaEventRecord(e2, s);
     if (!rc) rc = conv_tc(h, ta, B, s);
     cudaEventRecord(e3, s);
+    pmp::g_tc_scheme = -1;
     if (rc) return rc;
     split_to_f32_kernel<<<1024, 256, 0, s>>>(out, (float *)d_out32.p, B);
     cudaError_t ce = cudaStreamSynchronize(s);
