@@ -158,6 +158,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// for the roles that wait long (epilogue for a whole MMA phase, producers for a free slot): back off between probes
+// so the polling does not take issue slots (and power) from the MMA issuers
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) __nanosleep(100);
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int c0, int c1, int c2,
                                             int c3)
 {
@@ -402,7 +408,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
             for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
                 const uint8_t *src = wsrc;
                 for (int it = 0; it < per_item; it++, src += p.stage_bytes) {
-                    mbar_wait(bar_wempty + 8 * s, ph ^ 1u);
+                    mbar_wait_relaxed(bar_wempty + 8 * s, ph ^ 1u);
                     mbar_expect_tx(bar_wfull + 8 * s, p.stage_bytes);
                     bulk_g2s(smem_u32(ring) + s * p.stage_bytes, src, p.stage_bytes, bar_wfull + 8 * s);
                     if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1u; }
@@ -417,7 +423,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
             for (int item = blockIdx.x; item < p.items; item += gridDim.x, idx++) {
                 const TileGeom t = tile_geom(p, item);
                 for (int g = 0; g < p.groups; g++) {
-                    mbar_wait(bar_aempty + 8 * g, (idx & 1u) ^ 1u);
+                    mbar_wait_relaxed(bar_aempty + 8 * g, (idx & 1u) ^ 1u);
                     mbar_expect_tx(bar_afull + 8 * g, p.group_bytes);
                     tma_load_4d(smem_u32(act + (size_t)g * p.group_bytes), &tmap, bar_afull + 8 * g, -2 * p.padx,
                                 t.row0 - p.pady, g * 4, t.n);
@@ -541,7 +547,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
                 }
             }
             const uint32_t buf = idx & 1u;
-            mbar_wait(bar_acc + 8 * buf, (idx >> 1) & 1u);
+            mbar_wait_relaxed(bar_acc + 8 * buf, (idx >> 1) & 1u);
             tc_fence_after();
             for (int mt = 0; mt < t.mt_count; mt++) {
                 const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
