@@ -215,7 +215,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--engine", type=str, default="tc", choices=["tc", "simt"])
-    ap.add_argument("--chunk", type=int, default=1200)
+    ap.add_argument("--chunk", type=int, default=2400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     args = ap.parse_args()

@@ -55,7 +55,7 @@ static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W,
 {
     if (kh < 1 || kh > 9 || kw < 1 || kw > 5) return false;
     if (cin_pad % 16 || cout_pad % 16 || cin_pad < 16 || cout_pad < 16 || cout_pad > 64) return false;
-    if (H < 16 || W < 16 || (W & 1)) return false;
+    if (H < 8 || W < 8 || (W & 1)) return false;
     g.groups = cin_pad / 16;
     if (g.groups > TC_MAX_GROUPS) return false;
     g.coutp = cout_pad;

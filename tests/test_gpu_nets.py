@@ -124,3 +124,39 @@ def test_engines_agree_on_large_batch():
     assert max(float((a - b).abs().max()) for a, b in zip(o0, o1)) <= 1e-2
     q2 = netq(x[137:138])
     assert torch.equal(q2, q1[137:138])
+
+
+@pytest.mark.parametrize("cls", ["D", "C", "B", "A"])
+def test_mixed_class_shapes_integer_path(cls):
+    """BASELINE configs[4]: one frame of each VVC class shape through the whole pipeline.  The integer outputs must equal
+    the C-oracle decode of the GPU's own float maps bit for bit (blocks flagged as float32 near-ties excepted)."""
+    from oracle import c_decode
+    w, h = synth.CLASS_SHAPES[cls]
+    y, u, v = synth.synth_yuv420(w, h, 1, seed=40 + ord(cls))
+    pp = PartitionPredictor(0, engine="tc", chunk=700)
+    for comp in ("Luma", "Chroma"):
+        pp.load_state_dicts(comp, 37, load_reference_pkl(os.path.join(ROOT, "trained_models", "%s_Q_37.pkl" % comp)),
+                            synth.seeded_state_dict(comp + "_MSBD", cases.msbd_seed(comp, 37)))
+    res = pp.predict_frames(y, u, v, qps=(37,), want_maps=True)
+    bh, bw = h // 64, w // 64
+    for comp in ("Luma", "Chroma"):
+        vals, qt, bt, dire, flags = res[(comp, 37)]
+        assert vals.shape == (1, ops.frame_values(bh, bw)) and qt.shape[0] == bh * bw
+        assert torch.isfinite(qt).all() and torch.isfinite(bt).all() and torch.isfinite(dire).all()
+        qi = c_decode.qt_postprocess(qt.cpu().numpy())
+        hor, ver, dout = c_decode.map_to_partition_batch(qi[:, 0], bt.cpu().numpy(), dire.cpu().numpy(),
+                                                         1 if comp == "Luma" else 2)
+        R, C = bh * 16, bw * 16
+        got = vals.cpu().numpy().reshape(-1)
+        H = hor.reshape(bh, bw, 16, 16).transpose(0, 2, 1, 3).reshape(-1)
+        V = ver.reshape(bh, bw, 16, 16).transpose(0, 2, 1, 3).reshape(-1)
+        Q = qi[:, 0].astype(np.int8).reshape(bh, bw, 8, 8).transpose(0, 2, 1, 3).reshape(-1)
+        D = dout.reshape(bh, bw, 3, 16, 16).transpose(2, 0, 3, 1, 4).reshape(-1)
+        want = np.concatenate([H, V, Q, D]).astype(np.int8)
+        diff = np.nonzero(got != want)[0]
+        if diff.size:
+            fl = flags.cpu().numpy()
+            assert (fl & 1).any(), "%s %s: %d differing values and no near-tie flag" % (cls, comp, diff.size)
+            assert diff.size <= 3 * 768 * int((fl & 1).sum())
+        assert set(np.unique(got)) <= {-1, 0, 1, 2, 3}
+        assert got[:R * C].reshape(R, C)[::16].all()          # every block's top row is an edge

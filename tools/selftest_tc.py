@@ -9,7 +9,7 @@ CONFIGS = [  # cin, cout, k, hw, batch, flags (1 relu, 2 residual, 4 mul, 8 bf16
     (64, 64, 3, 64, 3, 0), (64, 64, 3, 64, 3, 3), (32, 64, 5, 64, 2, 1), (64, 64, 5, 64, 2, 3), (32, 64, 1, 64, 2, 0),
     (64, 64, 3, 32, 5, 3), (64, 64, 5, 32, 3, 3), (32, 64, 3, 32, 2, 7), (3, 32, 3, 32, 2, 1), (64, 32, 3, 32, 2, 1),
     (64, 32, 3, 16, 7, 1), (128, 32, 3, 16, 3, 1), (32, 32, 3, 16, 3, 3), (3, 32, 3, 16, 3, 1), (32, 64, 3, 16, 3, 7),
-    (32, 16, 3, 16, 3, 1), (16, 8, 3, 16, 3, 3), (64, 32, 1, 16, 3, 0), (16, 8, 1, 32, 2, 0), (64, 64, 3, 64, 2, 11),
+    (32, 16, 3, 16, 3, 1), (16, 8, 3, 16, 3, 3), (64, 32, 1, 16, 3, 0), (16, 8, 1, 32, 2, 0), (64, 64, 3, 64, 2, 11), (32, 8, 3, 8, 5, 1), (8, 8, 3, 8, 5, 3), (32, 8, 1, 8, 5, 0),
 ]
 
 
