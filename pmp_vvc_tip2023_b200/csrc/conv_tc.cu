@@ -34,7 +34,7 @@ namespace pmp {
 constexpr int TC_THREADS = 448;
 constexpr int TC_MMA_WARPS = 4;
 constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_MAX_STAGES = 12;
+constexpr int TC_MAX_STAGES = 24;
 constexpr int TC_MAX_GROUPS = 8;
 constexpr uint32_t TC_SMEM_HEADER = 1024;
 constexpr uint32_t TC_SMEM_MAX = 232448;          // 227 KB dynamic shared memory per CTA
@@ -50,6 +50,8 @@ struct TcGeom {
 //               4 M-tiles x 2 buffers when 16*Cout <= 512 (default for Cout <= 32, which are issue-bound), else
 //               2 M-tiles x 2 buffers with issuer pairs owning alternate tiles ("pairbuf"; measured slower, kept as an option).
 static int g_tc_scheme = -1;     // -1 auto, 0 unstacked, 1 stacked
+static int g_tc_pair = -1;       // -1 library default / env PMP_TC_PAIR, 0 single-CTA kernel, 1 CTA-pair kernel where applicable
+constexpr int TC_DEFAULT_PAIR = 1;
 
 static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W, TcGeom &g)
 {
@@ -132,6 +134,27 @@ void pack_tc_weights(const float *w, int cout, int cin, int kh, int kw, int cin_
                         dst[base + (size_t)n * 8 + e] = hi;
                         dst[base + (size_t)(cout_pad + n) * 8 + e] = lo;
                     }
+}
+
+// CTA-pair operand image: [rank (2)][group][tap][k8 (2)][64 rows: w_hi[32r..32r+32) then w_lo[32r..32r+32)][8] 16-bit
+size_t tc_pair_packed_elems(int cin_pad, int kh, int kw) { return (size_t)2 * (cin_pad / 16) * kh * kw * 2 * 64 * 8; }
+
+void pack_tc_pair_weights(const float *w, int cout, int cin, int kh, int kw, int cin_pad, bool bf16, uint16_t *dst)
+{
+    const int groups = cin_pad / 16, taps = kh * kw;
+    for (int r = 0; r < 2; r++)
+        for (int g = 0; g < groups; g++)
+            for (int t = 0; t < taps; t++)
+                for (int k8 = 0; k8 < 2; k8++)
+                    for (int n = 0; n < 32; n++)
+                        for (int e = 0; e < 8; e++) {
+                            const int c = g * 16 + k8 * 8 + e, co = 32 * r + n;
+                            uint16_t hi = 0, lo = 0;
+                            if (co < cout && c < cin) host_split(w[((size_t)co * cin + c) * taps + t], bf16, hi, lo);
+                            const size_t base = ((((size_t)r * groups + g) * taps + t) * 2 + k8) * 64 * 8;
+                            dst[base + (size_t)n * 8 + e] = hi;
+                            dst[base + (size_t)(32 + n) * 8 + e] = lo;
+                        }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -233,6 +256,7 @@ struct TcParams {
     int H, W, P, kh, kw, pady, padx, groups, total_mt, tiles, N1, coutp, nstages, items;
     uint32_t plane_bytes, group_bytes, stage_bytes, tmem_cols, idesc1, idesc2;
     int relu, stacked, pairbuf;
+    int B, pair_items;      // CTA-pair kernel: images in the batch, work items = tiles * ceil(B/2)
 };
 
 struct TileGeom { int n, mt_count, q0, row0, qoff; };
@@ -371,10 +395,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-    // barrier slots: [0,8) act_full, [8,16) act_empty, [16,28) w_full, [28,40) w_empty, [40,42) acc_full per accumulator buffer, [42,50) acc_empty per accumulator (buffer, M-tile)
+    // barrier slots: [0,8) act_full, [8,16) act_empty, [16,40) w_full, [40,64) w_empty, [64,66) acc_full per accumulator
+    // buffer, [66,74) acc_empty per accumulator (buffer, M-tile); TMEM base address at byte 1008
     const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + 8), bar_wfull = smem_u32(bars + 16),
-                   bar_wempty = smem_u32(bars + 28), bar_acc = smem_u32(bars + 40), bar_accempty = smem_u32(bars + 42);
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 512);
+                   bar_wempty = smem_u32(bars + 40), bar_acc = smem_u32(bars + 64), bar_accempty = smem_u32(bars + 66);
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 1008);
     uint8_t *act = smem + TC_SMEM_HEADER;
     uint8_t *ring = act + (size_t)p.groups * p.group_bytes;
 
@@ -390,7 +415,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + 512)),
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + 1008)),
                      "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -576,6 +601,281 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): the two CTAs of a cluster process the same tile index of two consecutive images.
+// One tcgen05.mma with M = 256 drives both SMs: each SM reads its own 128-position A tile and only HALF of the weight
+// operand (N/2 = 32 rows) from its shared memory -- the single-CTA kernel is bound by shared-memory operand reads
+// (18 KB per K=16 step, measured), the pair reads 15 KB.  Unstacked scheme only (Cout = 64), same tiling, TMEM double
+// buffering and warp roles as conv_tc_kernel; differences:
+//   * operands of BOTH CTAs are announced on the LEADER's (cluster rank 0) full barriers: the peer's TMA loads use
+//     .cta_group::2 with the leader's barrier address, the leader expects twice the bytes;
+//   * only the leader's four issuer warps issue MMAs; completion is multicast-committed to the empty / acc_full barriers
+//     of both CTAs; the epilogues of both CTAs report the TMEM drain to the leader's acc_empty barriers.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr)     // no fence: orders nothing but the count
+{
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap *tmap, uint32_t leader_bar, int c0, int c1,
+                                                 int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *tmap, uint32_t leader_bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar)       // arrives on `bar` (same offset) in both CTAs
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+constexpr uint32_t TC_PAIR_SLAB = 2048;      // per-CTA weight slab: [2 k8][32 w_hi rows | 32 w_lo rows][8] 16-bit
+
+struct PairGeom { int n, mt_count, q0, row0, qoff; bool store; };
+
+__device__ __forceinline__ PairGeom pair_geom(const TcParams &p, int item, int rank)
+{
+    PairGeom t;
+    const int pr = item / p.tiles, tl = item - pr * p.tiles;
+    const int n = 2 * pr + rank;
+    t.store = n < p.B;
+    t.n = t.store ? n : p.B - 1;          // odd batch: the peer recomputes the last image and drops the result
+    const int mt_begin = (tl * p.total_mt) / p.tiles, mt_end = ((tl + 1) * p.total_mt) / p.tiles;
+    t.mt_count = mt_end - mt_begin;
+    t.q0 = mt_begin * 128;
+    t.row0 = t.q0 / p.P;
+    t.qoff = t.q0 - t.row0 * p.P;
+    return t;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+    // same barrier slots as conv_tc_kernel
+    const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + 8), bar_wfull = smem_u32(bars + 16),
+                   bar_wempty = smem_u32(bars + 40), bar_acc = smem_u32(bars + 64), bar_accempty = smem_u32(bars + 66);
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 1008);
+    uint8_t *act = smem + TC_SMEM_HEADER;
+    uint8_t *ring = act + (size_t)p.groups * p.group_bytes;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+    const int taps = p.kh * p.kw;
+
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < p.groups; g++) { mbar_init(bar_afull + 8 * g, 1); mbar_init(bar_aempty + 8 * g, TC_MMA_WARPS); }
+        for (int s = 0; s < p.nstages; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, TC_MMA_WARPS); }
+        mbar_init(bar_acc, TC_MMA_WARPS);
+        mbar_init(bar_acc + 8, TC_MMA_WARPS);
+        for (int m = 0; m < 8; m++) mbar_init(bar_accempty + 8 * m, 2 * TC_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + 1008)),
+                     "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== weight producer: this CTA's half of every (group, tap) slab; bytes are counted on the leader =====
+            const int per_item = taps * p.groups;
+            const uint32_t lead_wfull = mapa_cluster(bar_wfull, 0);
+            uint32_t s = 0, ph = 0;
+            for (int item = cid; item < p.pair_items; item += ncl) {
+                for (int it = 0; it < per_item; it++) {
+                    mbar_wait_relaxed(bar_wempty + 8 * s, ph ^ 1u);
+                    if (rank == 0) mbar_expect_tx(bar_wfull + 8 * s, 2u * TC_PAIR_SLAB);
+                    tma_load_2d_pair(smem_u32(ring) + s * TC_PAIR_SLAB, &tmap_w, lead_wfull + 8 * s, 0,
+                                     (int)rank * per_item + it);
+                    if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== activation producer (own image), bytes counted on the leader's act_full =====
+            const uint32_t lead_afull = mapa_cluster(bar_afull, 0);
+            uint32_t idx = 0;
+            for (int item = cid; item < p.pair_items; item += ncl, idx++) {
+                const PairGeom t = pair_geom(p, item, (int)rank);
+                for (int g = 0; g < p.groups; g++) {
+                    mbar_wait_relaxed(bar_aempty + 8 * g, (idx & 1u) ^ 1u);
+                    if (rank == 0) mbar_expect_tx(bar_afull + 8 * g, 2u * p.group_bytes);
+                    tma_load_4d_pair(smem_u32(act + (size_t)g * p.group_bytes), &tmap, lead_afull + 8 * g, -2 * p.padx,
+                                     t.row0 - p.pady, g * 4, t.n);
+                }
+            }
+        }
+    } else if (warp < 2 + TC_MMA_WARPS) {
+        if (rank == 0) {
+            // ===== MMA issuers (leader only): warp 2+m owns M-tile m of BOTH CTAs' tiles =====
+            const int m = warp - 2;
+            const uint64_t desc_c = ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);
+            const uint64_t adesc_c = desc_c | ((uint64_t)(p.plane_bytes >> 4) << 16);
+            const uint64_t bdesc_c = desc_c | ((uint64_t)((64u * 16u) >> 4) << 16);          // LBO = 64 rows per k8
+            const uint32_t act16 = (smem_u32(act) >> 4) + (uint32_t)m * 128u, ring16 = smem_u32(ring) >> 4;
+            const uint32_t group16 = p.group_bytes >> 4, stage16 = TC_PAIR_SLAB >> 4, lo16 = (2u * p.plane_bytes) >> 4;
+            const uint32_t idesc = p.idesc1, wlo16 = 32u;                                    // this CTA's w_lo rows follow its 32 w_hi rows
+            const int KH = p.kh, K = p.kw, P = p.P, NS = p.nstages, G = p.groups;
+            uint32_t s = 0, ph = 0, idx = 0;
+            for (int item = cid; item < p.pair_items; item += ncl, idx++) {
+                const PairGeom t = pair_geom(p, item, 0);
+                const uint32_t buf = idx & 1u;
+                const bool mine = m < t.mt_count;
+                const uint32_t accidx = buf * 4u + (uint32_t)m;
+                const uint32_t d_tmem = tmem_base + accidx * (uint32_t)p.coutp;
+                mbar_wait(bar_accempty + 8 * accidx, ((idx >> 1) & 1u) ^ 1u);   // both CTAs drained it (tile idx-2)
+                tc_fence_after();
+                uint32_t acc = 0;
+                for (int g = 0; g < G; g++) {
+                    mbar_wait(bar_afull + 8 * g, idx & 1u);
+                    const uint32_t ag = act16 + (uint32_t)g * group16 + (uint32_t)t.qoff;
+                    for (int ky = 0; ky < KH; ky++) {
+                        uint32_t sj[5], pj[5];
+                        bool ok[5];
+                        {
+                            uint32_t s2 = s, ph2 = ph;
+#pragma unroll
+                            for (int j = 0; j < 5; j++) {
+                                if (j < K) {
+                                    sj[j] = s2; pj[j] = ph2;
+                                    ok[j] = mbar_try_wait(bar_wfull + 8 * s2, ph2);
+                                    if (++s2 == (uint32_t)NS) { s2 = 0; ph2 ^= 1u; }
+                                }
+                            }
+                            s = s2; ph = ph2;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 5; j++)
+                            if (j < K) while (!ok[j]) ok[j] = mbar_try_wait(bar_wfull + 8 * sj[j], pj[j]);
+                        tc_fence_after();
+                        if (elect_one_sync()) {
+                            if (mine) {
+                                const uint64_t ad0 = adesc_c | (uint64_t)(ag + (uint32_t)(ky * P));
+#pragma unroll
+                                for (int j = 0; j < 5; j++) {
+                                    if (j < K) {
+                                        const uint64_t ad = ad0 + (uint64_t)j;
+                                        const uint64_t bd = bdesc_c | (uint64_t)(ring16 + sj[j] * stage16);
+                                        umma_f16_pair(d_tmem, ad, bd, idesc, acc);                      // a_hi * w_hi
+                                        umma_f16_pair(d_tmem, ad, bd + (uint64_t)wlo16, idesc, 1u);     // a_hi * w_lo
+                                        umma_f16_pair(d_tmem, ad + (uint64_t)lo16, bd, idesc, 1u);      // a_lo * w_hi
+                                        umma_commit_pair(bar_wempty + 8 * sj[j]);
+                                        acc = 1u;
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 5; j++)
+                                    if (j < K) { mbar_arrive(bar_wempty + 8 * sj[j]); mbar_arrive_cluster_relaxed(mapa_cluster(bar_wempty + 8 * sj[j], 1)); }
+                            }
+                        }
+                        __syncwarp();
+                        acc = 1u;
+                    }
+                    if (elect_one_sync()) {
+                        if (mine) umma_commit_pair(bar_aempty + 8 * g);
+                        else { mbar_arrive(bar_aempty + 8 * g); mbar_arrive_cluster_relaxed(mapa_cluster(bar_aempty + 8 * g, 1)); }
+                    }
+                    __syncwarp();
+                }
+                if (elect_one_sync()) {
+                    if (mine) umma_commit_pair(bar_acc + 8 * buf);
+                    else { mbar_arrive(bar_acc + 8 * buf); mbar_arrive_cluster_relaxed(mapa_cluster(bar_acc + 8 * buf, 1)); }
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs, own accumulators; the drain is reported to the leader) =====
+        const int quarter = warp & 3, half = (warp - 2 - TC_MMA_WARPS) >> 2;
+        const int ch0 = half * 4;
+        const uint32_t lead_accempty = mapa_cluster(bar_accempty, 0);
+        uint32_t idx = 0;
+        for (int item = cid; item < p.pair_items; item += ncl, idx++) {
+            const PairGeom t = pair_geom(p, item, (int)rank);
+            if (p.res.p && (lane & 7) == 0) {
+                const size_t plane = (size_t)p.H * p.W;
+                for (int mt = 0; mt < t.mt_count; mt++) {
+                    const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
+                    const int r = pos / p.P, c = pos - r * p.P;
+                    if (c < p.W && r < p.H) {
+                        for (int j = 0; j < 4; j++) {
+                            const size_t o = ((size_t)t.n * (p.out.Cp >> 2) + split_plane(ch0 + j, 0)) * plane + (size_t)r * p.W + c;
+                            prefetch_l2(reinterpret_cast<const uint4 *>(p.res.p) + o);
+                            prefetch_l2(reinterpret_cast<const uint4 *>(p.res.p) + o + 2 * plane);
+                        }
+                    }
+                }
+            }
+            const uint32_t buf = idx & 1u;
+            mbar_wait_relaxed(bar_acc + 8 * buf, (idx >> 1) & 1u);
+            tc_fence_after();
+            for (int mt = 0; mt < 4; mt++) {
+                const uint32_t accidx = 4u * buf + (uint32_t)mt;
+                if (mt < t.mt_count) {
+                    const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
+                    const int r = pos / p.P, c = pos - r * p.P;
+                    const bool valid = t.store && (c < p.W) && (r < p.H);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + accidx * (uint32_t)p.coutp;
+                    epilogue_chunks<4>(p, taddr, ch0, t.n, r, c, valid);
+                    tc_fence_before();
+                }
+                __syncwarp();
+                if (lane == 0) {        // TMEM reads are complete (wait::ld); nothing else needs ordering with this arrival
+                    if (rank == 0) mbar_arrive(bar_accempty + 8 * accidx);
+                    else mbar_arrive_cluster_relaxed(lead_accempty + 8 * accidx);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -635,17 +935,49 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     p.items = g.tiles * B;
     p.plane_bytes = g.plane_bytes; p.group_bytes = g.group_bytes; p.stage_bytes = g.stage_bytes; p.tmem_cols = g.tmem_cols;
     const uint32_t fmt = a.in.bf16 ? 1u : 0u;
-    const uint32_t idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 4) << 24);
+    const uint32_t idesc_base_nom = (1u << 4) | (fmt << 7) | (fmt << 10);
+    const uint32_t idesc_base = idesc_base_nom | ((128u >> 4) << 24);
     p.idesc1 = idesc_base | ((uint32_t)(g.N1 >> 3) << 17);
     p.idesc2 = idesc_base | ((uint32_t)(g.coutp >> 3) << 17);
     p.relu = a.relu; p.stacked = g.stacked; p.pairbuf = g.pairbuf;
     static bool attr_set = false;
     if (!attr_set) {
         PMP_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
+        PMP_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
         attr_set = true;
     }
-    dim3 grid(p.items < h->num_sms ? p.items : h->num_sms);
     const double flops = a.flops_override > 0 ? a.flops_override * B : 2.0 * B * H * W * (double)a.out.C * a.in.C * a.kh * a.kw;
+    static const int env_pair = [] { const char *e = getenv("PMP_TC_PAIR"); return e ? atoi(e) : TC_DEFAULT_PAIR; }();
+    const int want_pair = g_tc_pair < 0 ? env_pair : g_tc_pair;
+    if (want_pair && a.w_pair && !g.stacked && g.coutp == 64 && !a.mul.p && !a.bias && B >= 2) {
+        // CTA-pair kernel: 2-D tensor map over this conv's per-CTA weight slabs
+        CUtensorMap tmap_w;
+        const cuuint64_t nslab = (cuuint64_t)2 * g.groups * a.kh * a.kw;
+        cuuint64_t wdim[2] = {TC_PAIR_SLAB / 8, nslab};
+        cuuint64_t wstr[1] = {TC_PAIR_SLAB};
+        cuuint32_t wbox[2] = {TC_PAIR_SLAB / 8, 1};
+        cuuint32_t west[2] = {1, 1};
+        cr = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void *)a.w_pair, wdim, wstr, wbox, west, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled (pair weights) failed (%d)", (int)cr);
+            return PMP_ERR_CUDA;
+        }
+        p.B = B;
+        p.pair_items = g.tiles * ((B + 1) / 2);
+        int ns = (int)((TC_SMEM_MAX - TC_SMEM_HEADER - g.act_bytes) / TC_PAIR_SLAB);
+        p.nstages = ns < TC_MAX_STAGES ? ns : TC_MAX_STAGES;
+        const uint32_t smem_pair = TC_SMEM_HEADER + g.act_bytes + (uint32_t)p.nstages * TC_PAIR_SLAB;
+        p.idesc1 = idesc_base_nom | ((uint32_t)(g.coutp >> 3) << 17) | ((256u >> 4) << 24);      // M = 256 across the pair
+        int nsm = h->num_sms & ~1;
+        int grid = 2 * p.pair_items < nsm ? 2 * p.pair_items : nsm;
+        ProfScope ps(h, PROF_CONV_TC, s, flops, 0);
+        conv_tc_pair_kernel<<<grid, TC_THREADS, smem_pair, s>>>(tmap, tmap_w, p);
+        h->launches++;
+        PMP_CUDA(cudaGetLastError());
+        return PMP_OK;
+    }
+    dim3 grid(p.items < h->num_sms ? p.items : h->num_sms);
     ProfScope ps(h, PROF_CONV_TC, s, flops, 0);
     conv_tc_kernel<<<grid, TC_THREADS, g.smem_bytes, s>>>(tmap, p);
     h->launches++;
@@ -803,7 +1135,7 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     for (auto &v : hres) v = 10.f * lcg(seed);
     for (auto &v : hmul) v = 1.5f * lcg(seed);
 
-    DevBuf d_in32, d_res32, d_mul32, d_in, d_res, d_mul, d_out, d_out32, d_ref32, d_wsimt, d_wtc;
+    DevBuf d_in32, d_res32, d_mul32, d_in, d_res, d_mul, d_out, d_out32, d_ref32, d_wsimt, d_wtc, d_wpair;
     const size_t sp_in = act_bytes(FMT_SPLIT, B, cin, H, W), sp_out = act_bytes(FMT_SPLIT, B, cout, H, W);
     if (d_in32.alloc(n_in * 4) || d_res32.alloc(n_out * 4) || d_mul32.alloc(n_out * 4) || d_in.alloc(sp_in) ||
         d_res.alloc(sp_out) || d_mul.alloc(sp_out) || d_out.alloc(sp_out) || d_out32.alloc(n_out * 4) ||
@@ -825,6 +1157,12 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     if (d_wsimt.alloc(ps.size() * 4) || d_wtc.alloc(pk.size() * 2)) return PMP_ERR_CUDA;
     PMP_CUDA(cudaMemcpy(d_wsimt.p, ps.data(), ps.size() * 4, cudaMemcpyHostToDevice));
     PMP_CUDA(cudaMemcpy(d_wtc.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    if (coutp == 64) {
+        std::vector<uint16_t> pp(tc_pair_packed_elems(cinp, ksize, ksize));
+        pack_tc_pair_weights(hw_.data(), cout, cin, ksize, ksize, cinp, bf, pp.data());
+        if (d_wpair.alloc(pp.size() * 2)) return PMP_ERR_CUDA;
+        PMP_CUDA(cudaMemcpy(d_wpair.p, pp.data(), pp.size() * 2, cudaMemcpyHostToDevice));
+    }
 
     auto mk = [&](void *p, int C) {
         Act a;
@@ -857,14 +1195,15 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     ta.in = in; ta.out = out;
     if (flags & 2) ta.res = res;
     if (flags & 4) ta.mul = mul;
-    ta.w = (const uint16_t *)d_wtc.p; ta.cin_pad = cinp; ta.cout_pad = coutp; ta.kh = ta.kw = ksize; ta.pad_t = ta.pad_l = ksize / 2; ta.relu = flags & 1; ta.pool = 1;
+    ta.w = (const uint16_t *)d_wtc.p; ta.w_pair = (const uint16_t *)d_wpair.p; ta.cin_pad = cinp; ta.cout_pad = coutp; ta.kh = ta.kw = ksize; ta.pad_t = ta.pad_l = ksize / 2; ta.relu = flags & 1; ta.pool = 1;
     pmp::g_tc_scheme = ((flags >> 8) & 3) - 1;          // 0: library default, 1: unstacked, 2: stacked
+    pmp::g_tc_pair = (flags >> 10) & 1 ? 1 : ((flags >> 11) & 1 ? 0 : -1);   // bit 10: CTA-pair kernel, bit 11: force single
     if (!tc_supported(cinp, coutp, ksize, ksize, H, W)) { pmp::g_tc_scheme = -1; set_error("selftest: scheme not supported"); return PMP_ERR_UNSUPPORTED; }
     rc = conv_tc(h, ta, B, s);          // warm-up (also first-launch overheads)
     cudaEventRecord(e2, s);
     if (!rc) rc = conv_tc(h, ta, B, s);
     cudaEventRecord(e3, s);
-    pmp::g_tc_scheme = -1;
+    pmp::g_tc_scheme = -1; pmp::g_tc_pair = -1;
     if (rc) return rc;
     split_to_f32_kernel<<<1024, 256, 0, s>>>(out, (float *)d_out32.p, B);
     cudaError_t ce = cudaStreamSynchronize(s);

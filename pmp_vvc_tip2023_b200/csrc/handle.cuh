@@ -13,6 +13,7 @@ struct ConvW {
     // TC engine (split precision): per (phase, tap): [kchunk][2*cout_pad][8] 16-bit; see conv_tc.cu
     uint16_t *w_tc_f16 = nullptr;
     uint16_t *w_tc_bf16 = nullptr;
+    uint16_t *w_pair_f16 = nullptr, *w_pair_bf16 = nullptr;   // CTA-pair kernel images (Cout = 64 only)
     int cin_pad = 0, cout_pad = 0;      // channel counts padded to multiples of 16
 };
 
