@@ -53,6 +53,12 @@ static int g_tc_scheme = -1;     // -1 auto, 0 unstacked, 1 stacked
 static int g_tc_pair = -1;       // -1 library default / env PMP_TC_PAIR, 0 single-CTA kernel, 1 CTA-pair kernel where applicable
 constexpr int TC_DEFAULT_PAIR = 1;
 
+static bool tc_pair_default()
+{
+    static const int env_pair = [] { const char *e = getenv("PMP_TC_PAIR"); return e ? atoi(e) : TC_DEFAULT_PAIR; }();
+    return (g_tc_pair < 0 ? env_pair : g_tc_pair) != 0;
+}
+
 static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W, TcGeom &g)
 {
     if (kh < 1 || kh > 9 || kw < 1 || kw > 5) return false;
@@ -70,7 +76,9 @@ static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W,
         return e ? atoi(e) : -1;
     }();
     const int scheme = g_tc_scheme < 0 ? env_scheme : g_tc_scheme;
-    g.stacked = scheme == 1 || (scheme < 0 && cout_pad <= 32);
+    // auto: when the CTA-pair kernel is the default every layer runs the unstacked arithmetic (the pair kernel's), also
+    // in the single-CTA fallback (batch of 1), so results do not depend on batch composition bit for bit
+    g.stacked = scheme == 1 || (scheme < 0 && cout_pad <= 32 && !tc_pair_default());
     g.pairbuf = g.stacked && 16 * cout_pad > 512;
     const int mt_max = g.pairbuf ? 2 : 4;
     for (int mt = (g.total_mt < mt_max ? g.total_mt : mt_max); mt >= 1; mt--) {
@@ -136,24 +144,24 @@ void pack_tc_weights(const float *w, int cout, int cin, int kh, int kw, int cin_
                     }
 }
 
-// CTA-pair operand image: [rank (2)][group][tap][k8 (2)][64 rows: w_hi[32r..32r+32) then w_lo[32r..32r+32)][8] 16-bit
-size_t tc_pair_packed_elems(int cin_pad, int kh, int kw) { return (size_t)2 * (cin_pad / 16) * kh * kw * 2 * 64 * 8; }
+// CTA-pair operand image: [rank (2)][group][tap][k8 (2)][Cout_pad rows: w_hi[h*r..h*r+h) then w_lo[h*r..h*r+h), h = Cout_pad/2][8]
+size_t tc_pair_packed_elems(int cin_pad, int cout_pad, int kh, int kw) { return (size_t)2 * (cin_pad / 16) * kh * kw * 2 * cout_pad * 8; }
 
-void pack_tc_pair_weights(const float *w, int cout, int cin, int kh, int kw, int cin_pad, bool bf16, uint16_t *dst)
+void pack_tc_pair_weights(const float *w, int cout, int cin, int kh, int kw, int cin_pad, int cout_pad, bool bf16, uint16_t *dst)
 {
-    const int groups = cin_pad / 16, taps = kh * kw;
+    const int groups = cin_pad / 16, taps = kh * kw, half = cout_pad / 2;
     for (int r = 0; r < 2; r++)
         for (int g = 0; g < groups; g++)
             for (int t = 0; t < taps; t++)
                 for (int k8 = 0; k8 < 2; k8++)
-                    for (int n = 0; n < 32; n++)
+                    for (int n = 0; n < half; n++)
                         for (int e = 0; e < 8; e++) {
-                            const int c = g * 16 + k8 * 8 + e, co = 32 * r + n;
+                            const int c = g * 16 + k8 * 8 + e, co = half * r + n;
                             uint16_t hi = 0, lo = 0;
                             if (co < cout && c < cin) host_split(w[((size_t)co * cin + c) * taps + t], bf16, hi, lo);
-                            const size_t base = ((((size_t)r * groups + g) * taps + t) * 2 + k8) * 64 * 8;
+                            const size_t base = ((((size_t)r * groups + g) * taps + t) * 2 + k8) * cout_pad * 8;
                             dst[base + (size_t)n * 8 + e] = hi;
-                            dst[base + (size_t)(32 + n) * 8 + e] = lo;
+                            dst[base + (size_t)(half + n) * 8 + e] = lo;
                         }
 }
 
@@ -257,6 +265,7 @@ struct TcParams {
     uint32_t plane_bytes, group_bytes, stage_bytes, tmem_cols, idesc1, idesc2;
     int relu, stacked, pairbuf;
     int B, pair_items;      // CTA-pair kernel: images in the batch, work items = tiles * ceil(B/2)
+    uint32_t pair_slab;     // CTA-pair kernel: bytes of one per-CTA weight slab
 };
 
 struct TileGeom { int n, mt_count, q0, row0, qoff; };
@@ -661,7 +670,7 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, u
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-constexpr uint32_t TC_PAIR_SLAB = 2048;      // per-CTA weight slab: [2 k8][32 w_hi rows | 32 w_lo rows][8] 16-bit
+// per-CTA weight slab: [2 k8][Cout/2 w_hi rows | Cout/2 w_lo rows][8] 16-bit = 32 * Cout bytes (p.pair_slab)
 
 struct PairGeom { int n, mt_count, q0, row0, qoff; bool store; };
 
@@ -724,8 +733,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             for (int item = cid; item < p.pair_items; item += ncl) {
                 for (int it = 0; it < per_item; it++) {
                     mbar_wait_relaxed(bar_wempty + 8 * s, ph ^ 1u);
-                    if (rank == 0) mbar_expect_tx(bar_wfull + 8 * s, 2u * TC_PAIR_SLAB);
-                    tma_load_2d_pair(smem_u32(ring) + s * TC_PAIR_SLAB, &tmap_w, lead_wfull + 8 * s, 0,
+                    if (rank == 0) mbar_expect_tx(bar_wfull + 8 * s, 2u * p.pair_slab);
+                    tma_load_2d_pair(smem_u32(ring) + s * p.pair_slab, &tmap_w, lead_wfull + 8 * s, 0,
                                      (int)rank * per_item + it);
                     if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1u; }
                 }
@@ -752,10 +761,10 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             const int m = warp - 2;
             const uint64_t desc_c = ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);
             const uint64_t adesc_c = desc_c | ((uint64_t)(p.plane_bytes >> 4) << 16);
-            const uint64_t bdesc_c = desc_c | ((uint64_t)((64u * 16u) >> 4) << 16);          // LBO = 64 rows per k8
+            const uint64_t bdesc_c = desc_c | ((uint64_t)(uint32_t)p.coutp << 16);               // LBO = Cout rows per k8 (16 B each)
             const uint32_t act16 = (smem_u32(act) >> 4) + (uint32_t)m * 128u, ring16 = smem_u32(ring) >> 4;
-            const uint32_t group16 = p.group_bytes >> 4, stage16 = TC_PAIR_SLAB >> 4, lo16 = (2u * p.plane_bytes) >> 4;
-            const uint32_t idesc = p.idesc1, wlo16 = 32u;                                    // this CTA's w_lo rows follow its 32 w_hi rows
+            const uint32_t group16 = p.group_bytes >> 4, stage16 = p.pair_slab >> 4, lo16 = (2u * p.plane_bytes) >> 4;
+            const uint32_t idesc = p.idesc1, wlo16 = (uint32_t)p.coutp >> 1;                 // this CTA's w_lo rows follow its w_hi rows
             const int KH = p.kh, K = p.kw, P = p.P, NS = p.nstages, G = p.groups;
             uint32_t s = 0, ph = 0, idx = 0;
             for (int item = cid; item < p.pair_items; item += ncl, idx++) {
@@ -829,21 +838,21 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     } else {
         // ===== epilogue (both CTAs, own accumulators; the drain is reported to the leader) =====
         const int quarter = warp & 3, half = (warp - 2 - TC_MMA_WARPS) >> 2;
-        const int ch0 = half * 4;
+        const int nchunk = p.coutp >> 3, chh = nchunk >> 1, ch0 = half * chh;
         const uint32_t lead_accempty = mapa_cluster(bar_accempty, 0);
         uint32_t idx = 0;
         for (int item = cid; item < p.pair_items; item += ncl, idx++) {
             const PairGeom t = pair_geom(p, item, (int)rank);
-            if (p.res.p && (lane & 7) == 0) {
+            if ((p.res.p || p.mul.p) && (lane & 7) == 0) {
                 const size_t plane = (size_t)p.H * p.W;
                 for (int mt = 0; mt < t.mt_count; mt++) {
                     const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
                     const int r = pos / p.P, c = pos - r * p.P;
                     if (c < p.W && r < p.H) {
-                        for (int j = 0; j < 4; j++) {
+                        for (int j = 0; j < chh; j++) {
                             const size_t o = ((size_t)t.n * (p.out.Cp >> 2) + split_plane(ch0 + j, 0)) * plane + (size_t)r * p.W + c;
-                            prefetch_l2(reinterpret_cast<const uint4 *>(p.res.p) + o);
-                            prefetch_l2(reinterpret_cast<const uint4 *>(p.res.p) + o + 2 * plane);
+                            if (p.res.p) { prefetch_l2(reinterpret_cast<const uint4 *>(p.res.p) + o); prefetch_l2(reinterpret_cast<const uint4 *>(p.res.p) + o + 2 * plane); }
+                            if (p.mul.p) { prefetch_l2(reinterpret_cast<const uint4 *>(p.mul.p) + o); prefetch_l2(reinterpret_cast<const uint4 *>(p.mul.p) + o + 2 * plane); }
                         }
                     }
                 }
@@ -858,7 +867,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     const int r = pos / p.P, c = pos - r * p.P;
                     const bool valid = t.store && (c < p.W) && (r < p.H);
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + accidx * (uint32_t)p.coutp;
-                    epilogue_chunks<4>(p, taddr, ch0, t.n, r, c, valid);
+                    if (chh == 4) epilogue_chunks<4>(p, taddr, ch0, t.n, r, c, valid);
+                    else
+                        for (int j = 0; j < chh; j++) epilogue_chunks<1>(p, taddr, ch0 + j, t.n, r, c, valid);
                     tc_fence_before();
                 }
                 __syncwarp();
@@ -947,15 +958,14 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         attr_set = true;
     }
     const double flops = a.flops_override > 0 ? a.flops_override * B : 2.0 * B * H * W * (double)a.out.C * a.in.C * a.kh * a.kw;
-    static const int env_pair = [] { const char *e = getenv("PMP_TC_PAIR"); return e ? atoi(e) : TC_DEFAULT_PAIR; }();
-    const int want_pair = g_tc_pair < 0 ? env_pair : g_tc_pair;
-    if (want_pair && a.w_pair && !g.stacked && g.coutp == 64 && !a.mul.p && !a.bias && B >= 2) {
+    if (tc_pair_default() && a.w_pair && !g.stacked && B >= 2) {
         // CTA-pair kernel: 2-D tensor map over this conv's per-CTA weight slabs
         CUtensorMap tmap_w;
         const cuuint64_t nslab = (cuuint64_t)2 * g.groups * a.kh * a.kw;
-        cuuint64_t wdim[2] = {TC_PAIR_SLAB / 8, nslab};
-        cuuint64_t wstr[1] = {TC_PAIR_SLAB};
-        cuuint32_t wbox[2] = {TC_PAIR_SLAB / 8, 1};
+        const uint32_t slab = 32u * (uint32_t)g.coutp;
+        cuuint64_t wdim[2] = {slab / 8, nslab};
+        cuuint64_t wstr[1] = {slab};
+        cuuint32_t wbox[2] = {slab / 8, 1};
         cuuint32_t west[2] = {1, 1};
         cr = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void *)a.w_pair, wdim, wstr, wbox, west, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -965,9 +975,14 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         }
         p.B = B;
         p.pair_items = g.tiles * ((B + 1) / 2);
-        int ns = (int)((TC_SMEM_MAX - TC_SMEM_HEADER - g.act_bytes) / TC_PAIR_SLAB);
+        // the pair kernel always runs the unstacked scheme: 4 M-tiles x 2 buffers x Cout columns
+        p.stacked = 0; p.pairbuf = 0; p.pair_slab = slab;
+        uint32_t pc = 32;
+        while (pc < 8u * (uint32_t)g.coutp) pc <<= 1;
+        p.tmem_cols = pc;
+        int ns = (int)((TC_SMEM_MAX - TC_SMEM_HEADER - g.act_bytes) / slab);
         p.nstages = ns < TC_MAX_STAGES ? ns : TC_MAX_STAGES;
-        const uint32_t smem_pair = TC_SMEM_HEADER + g.act_bytes + (uint32_t)p.nstages * TC_PAIR_SLAB;
+        const uint32_t smem_pair = TC_SMEM_HEADER + g.act_bytes + (uint32_t)p.nstages * slab;
         p.idesc1 = idesc_base_nom | ((uint32_t)(g.coutp >> 3) << 17) | ((256u >> 4) << 24);      // M = 256 across the pair
         int nsm = h->num_sms & ~1;
         int grid = 2 * p.pair_items < nsm ? 2 * p.pair_items : nsm;
@@ -1157,9 +1172,9 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     if (d_wsimt.alloc(ps.size() * 4) || d_wtc.alloc(pk.size() * 2)) return PMP_ERR_CUDA;
     PMP_CUDA(cudaMemcpy(d_wsimt.p, ps.data(), ps.size() * 4, cudaMemcpyHostToDevice));
     PMP_CUDA(cudaMemcpy(d_wtc.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
-    if (coutp == 64) {
-        std::vector<uint16_t> pp(tc_pair_packed_elems(cinp, ksize, ksize));
-        pack_tc_pair_weights(hw_.data(), cout, cin, ksize, ksize, cinp, bf, pp.data());
+    {
+        std::vector<uint16_t> pp(tc_pair_packed_elems(cinp, coutp, ksize, ksize));
+        pack_tc_pair_weights(hw_.data(), cout, cin, ksize, ksize, cinp, coutp, bf, pp.data());
         if (d_wpair.alloc(pp.size() * 2)) return PMP_ERR_CUDA;
         PMP_CUDA(cudaMemcpy(d_wpair.p, pp.data(), pp.size() * 2, cudaMemcpyHostToDevice));
     }

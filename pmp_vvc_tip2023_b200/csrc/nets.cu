@@ -128,7 +128,14 @@ static int build_stem_tc(WeightSet &ws, int net, const std::vector<ParamSpec> &s
     rc = dev_upload(ws, pk, &cw.w_tc_f16);
     if (rc) return rc;
     pack_tc_weights(wm.data(), cout, cu, kb, 1, cw.cin_pad, cw.cout_pad, true, pk.data());
-    return dev_upload(ws, pk, &cw.w_tc_bf16);
+    rc = dev_upload(ws, pk, &cw.w_tc_bf16);
+    if (rc) return rc;
+    std::vector<uint16_t> pp(tc_pair_packed_elems(cw.cin_pad, cw.cout_pad, kb, 1));
+    pack_tc_pair_weights(wm.data(), cout, cu, kb, 1, cw.cin_pad, cw.cout_pad, false, pp.data());
+    rc = dev_upload(ws, pp, &cw.w_pair_f16);
+    if (rc) return rc;
+    pack_tc_pair_weights(wm.data(), cout, cu, kb, 1, cw.cin_pad, cw.cout_pad, true, pp.data());
+    return dev_upload(ws, pp, &cw.w_pair_bf16);
 }
 
 int weights_create(Handle *h, int net, const float *const *tensors, const int64_t *numel, int n, int *wset)
@@ -182,12 +189,12 @@ int weights_create(Handle *h, int net, const float *const *tensors, const int64_
             if (rc) break;
             pack_tc_weights(tensors[i], co, ci, kh, kw, cw.cin_pad, cw.cout_pad, true, pk.data());
             rc = dev_upload(ws, pk, &cw.w_tc_bf16);
-            if (!rc && cw.cout_pad == 64) {
-                std::vector<uint16_t> pp(tc_pair_packed_elems(cw.cin_pad, kh, kw));
-                pack_tc_pair_weights(tensors[i], co, ci, kh, kw, cw.cin_pad, false, pp.data());
+            if (!rc) {
+                std::vector<uint16_t> pp(tc_pair_packed_elems(cw.cin_pad, cw.cout_pad, kh, kw));
+                pack_tc_pair_weights(tensors[i], co, ci, kh, kw, cw.cin_pad, cw.cout_pad, false, pp.data());
                 rc = dev_upload(ws, pp, &cw.w_pair_f16);
                 if (rc) break;
-                pack_tc_pair_weights(tensors[i], co, ci, kh, kw, cw.cin_pad, true, pp.data());
+                pack_tc_pair_weights(tensors[i], co, ci, kh, kw, cw.cin_pad, cw.cout_pad, true, pp.data());
                 rc = dev_upload(ws, pp, &cw.w_pair_bf16);
             }
         }
@@ -321,6 +328,7 @@ struct Net {
             rc = stem_unroll(h, x, qt, up, ov, w->kh, u, B, s);
             TcConvArgs a;
             a.in = u; a.out = out; a.w = wp; a.bias = w->bias;
+            a.w_pair = (h->tc_dtype == PMP_TC_BF16) ? w->w_pair_bf16 : w->w_pair_f16;
             a.cin_pad = w->cin_pad; a.cout_pad = w->cout_pad; a.kh = w->kh; a.kw = 1; a.pad_t = 0; a.pad_l = 0;
             a.Ho = out.H; a.relu = 1; a.pool = 1; a.flops_override = flops_per_image;
             if (!rc) rc = conv_tc(h, a, B, s);

@@ -124,6 +124,11 @@ def test_engines_agree_on_large_batch():
     assert max(float((a - b).abs().max()) for a, b in zip(o0, o1)) <= 1e-2
     q2 = netq(x[137:138])
     assert torch.equal(q2, q1[137:138])
+    # odd batch: the CTA-pair conv kernel's peer CTA recomputes the last image and must drop it
+    q3 = netq(x[:5])
+    assert torch.equal(q3, q1[:5])
+    o3 = netb(x[:5], q0[:5])
+    assert all(torch.equal(a, b[:5]) for a, b in zip(o3, o1))
 
 
 @pytest.mark.parametrize("cls", ["D", "C", "B", "A"])

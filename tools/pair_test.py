@@ -4,7 +4,8 @@ sys.path.insert(0, ".")
 from pmp_vvc_tip2023_b200 import _lib
 h = _lib.Handle.get(0); L = _lib.lib()
 nfail = 0
-for cin, cout, k, hw, b, fl in [(64, 64, 3, 64, 2, 1), (64, 64, 3, 64, 5, 3), (32, 64, 5, 64, 3, 1), (64, 64, 5, 32, 4, 3), (64, 64, 3, 32, 7, 3), (32, 64, 1, 64, 3, 0),
+for cin, cout, k, hw, b, fl in [(64, 32, 3, 32, 3, 1), (32, 16, 3, 16, 5, 3), (16, 8, 3, 16, 4, 3), (3, 32, 3, 16, 3, 1), (32, 64, 3, 32, 3, 7), (128, 32, 3, 16, 3, 1), (32, 8, 3, 8, 5, 1),
+                                (64, 32, 3, 32, 1776, 1), (64, 32, 3, 16, 3552, 1), (32, 16, 3, 16, 3552, 3), (32, 64, 3, 32, 1776, 7), (64, 64, 3, 64, 2, 1), (64, 64, 3, 64, 5, 3), (32, 64, 5, 64, 3, 1), (64, 64, 5, 32, 4, 3), (64, 64, 3, 32, 7, 3), (32, 64, 1, 64, 3, 0),
                                 (64, 64, 3, 64, 444, 3), (64, 64, 5, 64, 296, 3), (32, 64, 5, 64, 296, 1), (64, 64, 3, 32, 1776, 3)]:
     for mode, bit in (("single", 1 << 11), ("pair  ", 1 << 10)):
         me, am, t1, t2 = (ctypes.c_double() for _ in range(4))
