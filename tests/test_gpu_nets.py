@@ -165,3 +165,32 @@ def test_mixed_class_shapes_integer_path(cls):
             assert diff.size <= 3 * 768 * int((fl & 1).sum())
         assert set(np.unique(got)) <= {-1, 0, 1, 2, 3}
         assert got[:R * C].reshape(R, C)[::16].all()          # every block's top row is an edge
+
+
+def test_cli_driver_writes_reference_files(tmp_path):
+    """The mirrored Inference_QBD driver (same flags / output tree as the reference, Inference_QBD.py:152-255) on a tiny
+    10-bit sequence: the PartitionMat files must equal the ones the reference wrote for the same frames and weights."""
+    import argparse
+    y, u, v = cases.pipeline_frames()
+    inp = tmp_path / "in"
+    inp.mkdir()
+    with open(inp / "pipe_192x128_10bit.yuv", "wb") as fp:
+        for f in range(cases.PIPE_F):
+            fp.write(y[f].tobytes()); fp.write(u[f].tobytes()); fp.write(v[f].tobytes())
+    (tmp_path / "seqs.txt").write_text("pipe,pipe_192x128_10bit.yuv,192,128,%d,30\n#end!!!!\n" % cases.PIPE_F)
+    cfg = tmp_path / "cfg"
+    cfg.mkdir()
+    (cfg / "pipe.cfg").write_text("InputFile : %s # comment\nInputBitDepth : 10\n" % (inp / "pipe_192x128_10bit.yuv"))
+    args = Inference_QBD.build_parser().parse_args([
+        "--jobID", "j1", "--inputDir", str(inp), "--outDir", str(tmp_path / "out"), "--batchSize", "5", "--startSeqID", "0",
+        "--seqNum", "1", "--seqInfo", str(tmp_path / "seqs.txt"), "--cfgDir", str(cfg),
+        "--modelDir", os.path.join(ROOT, "trained_models"), "--ssRatio", "1", "--missingBD", "seeded"])
+    Inference_QBD.inference_VVC_seqs(args)
+    out = tmp_path / "out" / "j1" / "PartitionMat"
+    names = sorted(os.listdir(out))
+    assert len(names) == 8 and "pipe_192x128_10bit_Luma_QP32_PartitionMat.txt" in names
+    for comp in ("Luma", "Chroma"):
+        got = open(out / ("pipe_192x128_10bit_%s_QP32_PartitionMat.txt" % comp), "rb").read()
+        want = open(os.path.join(GOLDEN, "pipeline_%s_QP32_PartitionMat.txt" % comp), "rb").read()
+        assert got == want
+    assert os.path.exists(tmp_path / "out" / "j1" / "Time_Sta_0_1.txt")
