@@ -76,7 +76,6 @@ int ensure_arena(Handle *h, size_t bytes)
         PMP_CUDA(cudaFree(h->arena));
         h->arena = nullptr;
         h->arena_bytes = 0;
-        h->tmaps.clear();
     }
     bytes = (bytes + ((size_t)1 << 21)) & ~(((size_t)1 << 21) - 1);
     PMP_CUDA(cudaMalloc((void **)&h->arena, bytes));

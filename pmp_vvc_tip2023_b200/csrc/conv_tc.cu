@@ -17,8 +17,10 @@
 // P-W pad columns compute garbage that the epilogue drops (W/P = 94..97 % efficiency).  Weights stream through a
 // shared-memory ring, one (tap, channel-group) slab [2][N][8] per stage via cp.async.bulk, pre-packed on the host.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 = epilogue (TMEM -> registers ->
-// residual add / ReLU / attention product -> hi/lo split -> coalesced 16-byte stores); warp 2 owns the TMEM allocation.
+// Warp roles (448 threads, persistent grid): warp 0 = weight producer, warp 1 = activation producer + TMEM owner,
+// warps 2-5 = MMA issuers (one per M-tile), warps 6-13 = epilogue (TMEM -> registers -> bias / residual add / ReLU /
+// attention product -> hi/lo split -> coalesced 16-byte stores).  Two kernels: conv_tc_kernel (one CTA per SM) and
+// conv_tc_pair_kernel (cta_group::2 CTA pairs, the default whenever the batch has at least two images).
 #include "handle.cuh"
 #include "kernels.cuh"
 
@@ -916,7 +918,7 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     TcGeom g;
     const int H = a.Ho ? a.Ho : a.in.H, W = a.in.W, Hin = a.in.H;
     if (a.in.fmt != FMT_SPLIT || a.out.fmt != FMT_SPLIT || !tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g) ||
-        a.in.Cp != a.cin_pad || a.out.Cp != a.cout_pad || a.pool != 1 || a.in2.p || a.out.H != H || a.out.W != W) {
+        a.in.Cp != a.cin_pad || a.out.Cp != a.cout_pad || a.pool != 1 || a.out.H != H || a.out.W != W) {
         set_error("conv_tc: unsupported configuration cin %d cout %d k %dx%d %dx%d", a.cin_pad, a.cout_pad, a.kh, a.kw, H, W);
         return PMP_ERR_UNSUPPORTED;
     }

@@ -10,7 +10,7 @@ struct ConvW {
     int cout = 0, cin = 0, kh = 0, kw = 0;
     float *w_simt = nullptr;     // [cin][kh][kw][cout_pad4]  fp32 (SIMT engine; cout innermost)
     float *bias = nullptr;       // [cout] or nullptr
-    // TC engine (split precision): per (phase, tap): [kchunk][2*cout_pad][8] 16-bit; see conv_tc.cu
+    // TC engine (split precision) operand images, see pack_tc_weights / pack_tc_pair_weights in conv_tc.cu
     uint16_t *w_tc_f16 = nullptr;
     uint16_t *w_tc_bf16 = nullptr;
     uint16_t *w_pair_f16 = nullptr, *w_pair_bf16 = nullptr;   // CTA-pair kernel images (Cout = 64 only)
@@ -45,8 +45,6 @@ struct Handle {
     size_t scratch_bytes = 0;
     // driver entry point for tensor-map encoding (resolved lazily; avoids linking libcuda)
     void *encode_tiled = nullptr;
-    // cached tensor maps keyed by (ptr, dims...)
-    std::map<std::string, CUtensorMap> tmaps;
 };
 
 int ensure_arena(Handle *h, size_t bytes);

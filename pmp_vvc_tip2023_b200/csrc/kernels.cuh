@@ -28,15 +28,13 @@ int pool2_split(Handle *h, const Act &in, const Act &out, const Act &mul, int B,
 // ---- TC engine (conv_tc.cu) ------------------------------------------------------------------
 struct TcConvArgs {
     Act in;                 // FMT_SPLIT [B, cin_pad, H, W]
-    Act in2;                // optional second K phase: 1x1 shortcut conv over the block input (p == nullptr: none)
     Act out;                // FMT_SPLIT
     Act res;                // optional identity residual (FMT_SPLIT, same shape as the conv output)
     Act mul;                // optional attention product (FMT_SPLIT, shape of the stored output)
     const uint16_t *w = nullptr;    // packed main weights (see pack_tc_weights)
-    const uint16_t *w2 = nullptr;   // packed 1x1 shortcut weights
     const uint16_t *w_pair = nullptr;   // CTA-pair operand image or nullptr
     const float *bias = nullptr;    // [cout_pad] fp32 or nullptr (stems only)
-    int cin_pad = 0, cin2_pad = 0, cout_pad = 0, kh = 1, kw = 1;
+    int cin_pad = 0, cout_pad = 0, kh = 1, kw = 1;
     int pad_t = 0, pad_l = 0;       // input coordinate = output coordinate + tap - pad
     int Ho = 0;                     // output rows (0: same as the input)
     int relu = 0, pool = 1;

@@ -8,9 +8,10 @@
 // lives in pmp_vvc_tip2023_b200/netspec.py for the Python side.
 //
 // Engine selection per layer: PMP_ENGINE_TC runs every square 1x1/3x3/5x5 conv whose input is a split-precision
-// activation on the tcgen05 kernel (conv_tc.cu) and keeps activations in FMT_SPLIT; the stems (Cin <= 4, 9x9/5x5
-// valid convs on pixels), the Cout <= 2 output convs and anything the TC kernel does not cover run on the exact
-// fp32 SIMT kernel, which reads/writes the same activation formats.  PMP_ENGINE_SIMT runs everything in fp32 NCHW.
+// activation on the tcgen05 kernels (conv_tc.cu) and keeps activations in FMT_SPLIT; the first-layer valid convs run
+// there too after their kx taps are unrolled into channels (stem_tc below); the Cout <= 2 output convs (bias, fp32
+// outputs) run on the exact fp32 SIMT kernel, which reads/writes the same activation formats.  PMP_ENGINE_SIMT runs
+// everything in fp32 NCHW.
 #include "handle.cuh"
 #include "kernels.cuh"
 

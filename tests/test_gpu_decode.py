@@ -163,3 +163,41 @@ def test_cut_blocks_pipeline_golden():
     lb, cb = ops.cut_blocks(tv(y), tv(u), tv(v))
     assert np.array_equal(lb[:, 0].cpu().numpy(), g["by"])
     assert np.array_equal(cb[:, 1].cpu().numpy(), g["bu"]) and np.array_equal(cb[:, 2].cpu().numpy(), g["bv"])
+
+
+def test_abi_error_paths():
+    """Error behaviour of the C ABI: negative status + message, no exceptions, no crash (GPU present)."""
+    import ctypes
+    from pmp_vvc_tip2023_b200 import _lib
+    h = _lib.Handle.get(0)
+    L = _lib.lib()
+    buf = torch.zeros(64, device="cuda")
+    # unknown weight set
+    rc = L.pmp_forward_q(h.ptr, 987654, buf.data_ptr(), _lib.IN_F32, 1, buf.data_ptr(), None)
+    assert rc == -4 and b"unknown weight set" in L.pmp_last_error()
+    # wrong tensor count / sizes for a net
+    arr = np.zeros(10, np.float32)
+    ptrs = (ctypes.c_void_p * 1)(arr.ctypes.data)
+    numel = (ctypes.c_int64 * 1)(10)
+    wset = ctypes.c_int(-1)
+    assert L.pmp_weights_create(h.ptr, 0, ptrs, numel, 1, ctypes.byref(wset)) == -1
+    with pytest.raises(_lib.PmpError):
+        h.weights_create("Luma_Q", [np.zeros(3, np.float32)] * 20)
+    # null pointers, bad chroma factor, negative batch
+    assert L.pmp_qt_postprocess(h.ptr, None, 4, None, None, None) == -1
+    assert L.pmp_map2partition(h.ptr, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), 1, 3, buf.data_ptr(), buf.data_ptr(),
+                               buf.data_ptr(), None, None) == -1
+    assert L.pmp_forward_q(h.ptr, 1, buf.data_ptr(), _lib.IN_F32, -1, buf.data_ptr(), None) == -1
+    # empty batches are no-ops
+    assert L.pmp_forward_q(h.ptr, 987654, None, _lib.IN_F32, 0, None, None) == 0
+    assert L.pmp_assemble_frames(h.ptr, None, None, None, None, 0, 3, 4, None, None) == 0
+    # a Q weight set is refused by the MSBD entry point
+    sd = synth.seeded_state_dict("Luma_Q", 1)
+    wq = h.weights_create("Luma_Q", list(sd.values()))
+    x = torch.zeros((1, 1, 68, 68), device="cuda")
+    o = torch.zeros((1, 2, 16, 16), device="cuda")
+    rc = L.pmp_forward_msbd(h.ptr, wq, x.data_ptr(), _lib.IN_F32, buf.data_ptr(), 1, o.data_ptr(), o.data_ptr(), o.data_ptr(), None)
+    assert rc == -4
+    h.weights_destroy(wq)
+    with pytest.raises(_lib.PmpError):
+        h.weights_destroy(wq)
