@@ -54,6 +54,8 @@ struct TcGeom {
 static int g_tc_scheme = -1;     // -1 auto, 0 unstacked, 1 stacked
 static int g_tc_pair = -1;       // -1 library default / env PMP_TC_PAIR, 0 single-CTA kernel, 1 CTA-pair kernel where applicable
 constexpr int TC_DEFAULT_PAIR = 1;
+static int g_tc_pair_st = -1;    // -1 library default / env PMP_TC_PAIR_STACKED: stacked accumulators in the pair kernel (Cout = 64)
+constexpr int TC_DEFAULT_PAIR_STACKED = 0;
 
 static bool tc_pair_default()
 {
@@ -61,7 +63,7 @@ static bool tc_pair_default()
     return (g_tc_pair < 0 ? env_pair : g_tc_pair) != 0;
 }
 
-static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W, TcGeom &g)
+static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W, TcGeom &g, int scheme_override = -1)
 {
     if (kh < 1 || kh > 9 || kw < 1 || kw > 5) return false;
     if (cin_pad % 16 || cout_pad % 16 || cin_pad < 16 || cout_pad < 16 || cout_pad > 64) return false;
@@ -77,7 +79,7 @@ static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W,
         const char *e = getenv("PMP_TC_SCHEME");       // tuning/A-B knob: 0 unstacked, 1 stacked
         return e ? atoi(e) : -1;
     }();
-    const int scheme = g_tc_scheme < 0 ? env_scheme : g_tc_scheme;
+    const int scheme = scheme_override >= 0 ? scheme_override : (g_tc_scheme < 0 ? env_scheme : g_tc_scheme);
     // auto: when the CTA-pair kernel is the default every layer runs the unstacked arithmetic (the pair kernel's), also
     // in the single-CTA fallback (batch of 1), so results do not depend on batch composition bit for bit
     g.stacked = scheme == 1 || (scheme < 0 && cout_pad <= 32 && !tc_pair_default());
@@ -164,6 +166,29 @@ void pack_tc_pair_weights(const float *w, int cout, int cin, int kh, int kw, int
                             const size_t base = ((((size_t)r * groups + g) * taps + t) * 2 + k8) * cout_pad * 8;
                             dst[base + (size_t)n * 8 + e] = hi;
                             dst[base + (size_t)(half + n) * 8 + e] = lo;
+                        }
+}
+
+// Stacked CTA-pair operand image (Cout = 64): per CTA rank r a slab [k8 (2)][96 rows][8]:
+//   rows  0..63 : this CTA's half of the N = 128 operand [w_hi | w_lo]  (rank 0: w_hi[0..64), rank 1: w_lo[0..64))
+//   rows 64..95 : this CTA's half of the N = 64 operand w_hi            (w_hi[32r .. 32r+32))
+size_t tc_pair_stacked_elems(int cin_pad, int kh, int kw) { return (size_t)2 * (cin_pad / 16) * kh * kw * 2 * 96 * 8; }
+
+void pack_tc_pair_stacked_weights(const float *w, int cout, int cin, int kh, int kw, int cin_pad, bool bf16, uint16_t *dst)
+{
+    const int groups = cin_pad / 16, taps = kh * kw;
+    for (int r = 0; r < 2; r++)
+        for (int g = 0; g < groups; g++)
+            for (int t = 0; t < taps; t++)
+                for (int k8 = 0; k8 < 2; k8++)
+                    for (int n = 0; n < 64; n++)
+                        for (int e = 0; e < 8; e++) {
+                            const int c = g * 16 + k8 * 8 + e;
+                            uint16_t hi = 0, lo = 0;
+                            if (n < cout && c < cin) host_split(w[((size_t)n * cin + c) * taps + t], bf16, hi, lo);
+                            const size_t base = ((((size_t)r * groups + g) * taps + t) * 2 + k8) * 96 * 8;
+                            dst[base + (size_t)n * 8 + e] = r == 0 ? hi : lo;
+                            if ((n >> 5) == r) dst[base + (size_t)(64 + (n & 31)) * 8 + e] = hi;
                         }
 }
 
@@ -268,6 +293,7 @@ struct TcParams {
     int relu, stacked, pairbuf;
     int B, pair_items;      // CTA-pair kernel: images in the batch, work items = tiles * ceil(B/2)
     uint32_t pair_slab;     // CTA-pair kernel: bytes of one per-CTA weight slab
+    int pair_box_rows;      // CTA-pair kernel: rows of the weight tensor map covered by one slab (1 or 2)
 };
 
 struct TileGeom { int n, mt_count, q0, row0, qoff; };
@@ -711,8 +737,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     if (threadIdx.x == 0) {
         for (int g = 0; g < p.groups; g++) { mbar_init(bar_afull + 8 * g, 1); mbar_init(bar_aempty + 8 * g, TC_MMA_WARPS); }
         for (int s = 0; s < p.nstages; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, TC_MMA_WARPS); }
-        mbar_init(bar_acc, TC_MMA_WARPS);
-        mbar_init(bar_acc + 8, TC_MMA_WARPS);
+        mbar_init(bar_acc, p.pairbuf ? 2 : TC_MMA_WARPS);
+        mbar_init(bar_acc + 8, p.pairbuf ? 2 : TC_MMA_WARPS);
         for (int m = 0; m < 8; m++) mbar_init(bar_accempty + 8 * m, 2 * TC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -737,7 +763,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     mbar_wait_relaxed(bar_wempty + 8 * s, ph ^ 1u);
                     if (rank == 0) mbar_expect_tx(bar_wfull + 8 * s, 2u * p.pair_slab);
                     tma_load_2d_pair(smem_u32(ring) + s * p.pair_slab, &tmap_w, lead_wfull + 8 * s, 0,
-                                     (int)rank * per_item + it);
+                                     ((int)rank * per_item + it) * p.pair_box_rows);
                     if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -759,24 +785,32 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         }
     } else if (warp < 2 + TC_MMA_WARPS) {
         if (rank == 0) {
-            // ===== MMA issuers (leader only): warp 2+m owns M-tile m of BOTH CTAs' tiles =====
+            // ===== MMA issuers (leader only).  Default: warp 2+m owns M-tile m of BOTH CTAs' tiles (accumulator buf*4+m).
+            //       pairbuf (stacked, Cout = 64): tiles have 2 M-tiles; warp 2+m owns M-tile m&1 of the tiles whose
+            //       accumulator buffer is m>>1, the other two issuers only walk the barriers. =====
             const int m = warp - 2;
+            const int mym = p.pairbuf ? (m & 1) : m;
             const uint64_t desc_c = ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);
             const uint64_t adesc_c = desc_c | ((uint64_t)(p.plane_bytes >> 4) << 16);
-            const uint64_t bdesc_c = desc_c | ((uint64_t)(uint32_t)p.coutp << 16);               // LBO = Cout rows per k8 (16 B each)
-            const uint32_t act16 = (smem_u32(act) >> 4) + (uint32_t)m * 128u, ring16 = smem_u32(ring) >> 4;
+            const uint64_t bdesc_c = desc_c | ((uint64_t)(p.pair_slab >> 5) << 16);              // LBO = slab rows per k8 (16 B each)
+            const uint32_t act16 = (smem_u32(act) >> 4) + (uint32_t)mym * 128u, ring16 = smem_u32(ring) >> 4;
             const uint32_t group16 = p.group_bytes >> 4, stage16 = p.pair_slab >> 4, lo16 = (2u * p.plane_bytes) >> 4;
-            const uint32_t idesc = p.idesc1, wlo16 = (uint32_t)p.coutp >> 1;                 // this CTA's w_lo rows follow its w_hi rows
+            const uint32_t idesc = p.idesc1, idesc_st = p.idesc2;
+            const uint32_t wlo16 = (uint32_t)p.coutp >> 1;      // unstacked: this CTA's w_lo rows follow its w_hi rows
+            const uint32_t b2_16 = (uint32_t)p.coutp;           // stacked: rows of the N = Cout operand follow the N = 2*Cout half
             const int KH = p.kh, K = p.kw, P = p.P, NS = p.nstages, G = p.groups;
             uint32_t s = 0, ph = 0, idx = 0;
             for (int item = cid; item < p.pair_items; item += ncl, idx++) {
                 const PairGeom t = pair_geom(p, item, 0);
                 const uint32_t buf = idx & 1u;
-                const bool mine = m < t.mt_count;
-                const uint32_t accidx = buf * 4u + (uint32_t)m;
-                const uint32_t d_tmem = tmem_base + accidx * (uint32_t)p.coutp;
-                mbar_wait(bar_accempty + 8 * accidx, ((idx >> 1) & 1u) ^ 1u);   // both CTAs drained it (tile idx-2)
-                tc_fence_after();
+                const bool owner = !p.pairbuf || (uint32_t)(m >> 1) == buf;
+                const bool mine = owner && mym < t.mt_count;
+                const uint32_t accidx = p.pairbuf ? (uint32_t)m : buf * 4u + (uint32_t)m;
+                const uint32_t d_tmem = tmem_base + accidx * (uint32_t)(p.stacked ? p.N1 : p.coutp);
+                if (owner) {
+                    mbar_wait(bar_accempty + 8 * accidx, ((idx >> 1) & 1u) ^ 1u);   // both CTAs drained it (tile idx-2)
+                    tc_fence_after();
+                }
                 uint32_t acc = 0;
                 for (int g = 0; g < G; g++) {
                     mbar_wait(bar_afull + 8 * g, idx & 1u);
@@ -808,9 +842,14 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                                     if (j < K) {
                                         const uint64_t ad = ad0 + (uint64_t)j;
                                         const uint64_t bd = bdesc_c | (uint64_t)(ring16 + sj[j] * stage16);
-                                        umma_f16_pair(d_tmem, ad, bd, idesc, acc);                      // a_hi * w_hi
-                                        umma_f16_pair(d_tmem, ad, bd + (uint64_t)wlo16, idesc, 1u);     // a_hi * w_lo
-                                        umma_f16_pair(d_tmem, ad + (uint64_t)lo16, bd, idesc, 1u);      // a_lo * w_hi
+                                        if (p.stacked) {
+                                            umma_f16_pair(d_tmem, ad, bd, idesc_st, acc);                               // a_hi * [w_hi | w_lo]
+                                            umma_f16_pair(d_tmem, ad + (uint64_t)lo16, bd + (uint64_t)b2_16, idesc, 1u);  // a_lo * w_hi
+                                        } else {
+                                            umma_f16_pair(d_tmem, ad, bd, idesc, acc);                      // a_hi * w_hi
+                                            umma_f16_pair(d_tmem, ad, bd + (uint64_t)wlo16, idesc, 1u);     // a_hi * w_lo
+                                            umma_f16_pair(d_tmem, ad + (uint64_t)lo16, bd, idesc, 1u);      // a_lo * w_hi
+                                        }
                                         umma_commit_pair(bar_wempty + 8 * sj[j]);
                                         acc = 1u;
                                     }
@@ -830,7 +869,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     }
                     __syncwarp();
                 }
-                if (elect_one_sync()) {
+                if (owner && elect_one_sync()) {
                     if (mine) umma_commit_pair(bar_acc + 8 * buf);
                     else { mbar_arrive(bar_acc + 8 * buf); mbar_arrive_cluster_relaxed(mapa_cluster(bar_acc + 8 * buf, 1)); }
                 }
@@ -862,13 +901,14 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             const uint32_t buf = idx & 1u;
             mbar_wait_relaxed(bar_acc + 8 * buf, (idx >> 1) & 1u);
             tc_fence_after();
-            for (int mt = 0; mt < 4; mt++) {
-                const uint32_t accidx = 4u * buf + (uint32_t)mt;
+            const int nmt = p.pairbuf ? 2 : 4;
+            for (int mt = 0; mt < nmt; mt++) {
+                const uint32_t accidx = (uint32_t)nmt * buf + (uint32_t)mt;
                 if (mt < t.mt_count) {
                     const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
                     const int r = pos / p.P, c = pos - r * p.P;
                     const bool valid = t.store && (c < p.W) && (r < p.H);
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + accidx * (uint32_t)p.coutp;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + accidx * (uint32_t)(p.stacked ? p.N1 : p.coutp);
                     if (chh == 4) epilogue_chunks<4>(p, taddr, ch0, t.n, r, c, valid);
                     else
                         for (int j = 0; j < chh; j++) epilogue_chunks<1>(p, taddr, ch0 + j, t.n, r, c, valid);
@@ -917,7 +957,10 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     if (B <= 0) return PMP_OK;
     TcGeom g;
     const int H = a.Ho ? a.Ho : a.in.H, W = a.in.W, Hin = a.in.H;
-    if (a.in.fmt != FMT_SPLIT || a.out.fmt != FMT_SPLIT || !tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g) ||
+    // CTA-pair kernel with stacked accumulators (Cout = 64): 2-M-tile tiles, geometry of the stacked/pairbuf scheme
+    static const int env_pair_st = [] { const char *e = getenv("PMP_TC_PAIR_STACKED"); return e ? atoi(e) : TC_DEFAULT_PAIR_STACKED; }();
+    const bool pair_st = tc_pair_default() && (g_tc_pair_st < 0 ? env_pair_st : g_tc_pair_st) && a.w_pair_st && a.cout_pad == 64 && B >= 2;
+    if (a.in.fmt != FMT_SPLIT || a.out.fmt != FMT_SPLIT || !tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g, pair_st ? 1 : -1) ||
         a.in.Cp != a.cin_pad || a.out.Cp != a.cout_pad || a.pool != 1 || a.out.H != H || a.out.W != W) {
         set_error("conv_tc: unsupported configuration cin %d cout %d k %dx%d %dx%d", a.cin_pad, a.cout_pad, a.kh, a.kw, H, W);
         return PMP_ERR_UNSUPPORTED;
@@ -960,25 +1003,27 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         attr_set = true;
     }
     const double flops = a.flops_override > 0 ? a.flops_override * B : 2.0 * B * H * W * (double)a.out.C * a.in.C * a.kh * a.kw;
-    if (tc_pair_default() && a.w_pair && !g.stacked && B >= 2) {
-        // CTA-pair kernel: 2-D tensor map over this conv's per-CTA weight slabs
+    if (tc_pair_default() && B >= 2 && (pair_st || (a.w_pair && !g.stacked))) {
+        // CTA-pair kernel: 2-D tensor map over this conv's per-CTA weight slabs (8-byte elements, <= 256 per box row)
         CUtensorMap tmap_w;
         const cuuint64_t nslab = (cuuint64_t)2 * g.groups * a.kh * a.kw;
-        const uint32_t slab = 32u * (uint32_t)g.coutp;
-        cuuint64_t wdim[2] = {slab / 8, nslab};
-        cuuint64_t wstr[1] = {slab};
-        cuuint32_t wbox[2] = {slab / 8, 1};
+        const uint32_t slab = pair_st ? 3072u : 32u * (uint32_t)g.coutp;
+        const uint32_t box_rows = slab / 8 > 256 ? 2u : 1u, row_bytes = slab / box_rows;
+        cuuint64_t wdim[2] = {row_bytes / 8, nslab * box_rows};
+        cuuint64_t wstr[1] = {row_bytes};
+        cuuint32_t wbox[2] = {row_bytes / 8, box_rows};
         cuuint32_t west[2] = {1, 1};
-        cr = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void *)a.w_pair, wdim, wstr, wbox, west, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        cr = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void *)(pair_st ? a.w_pair_st : a.w_pair), wdim, wstr, wbox, west,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) {
             set_error("cuTensorMapEncodeTiled (pair weights) failed (%d)", (int)cr);
             return PMP_ERR_CUDA;
         }
         p.B = B;
         p.pair_items = g.tiles * ((B + 1) / 2);
-        // the pair kernel always runs the unstacked scheme: 4 M-tiles x 2 buffers x Cout columns
-        p.stacked = 0; p.pairbuf = 0; p.pair_slab = slab;
+        // unstacked: 4 M-tiles x 2 buffers x Cout columns; stacked (Cout = 64): 2 M-tiles x 2 buffers x 2*Cout columns
+        p.stacked = pair_st ? 1 : 0; p.pairbuf = pair_st ? 1 : 0; p.pair_slab = slab; p.pair_box_rows = (int)box_rows;
         uint32_t pc = 32;
         while (pc < 8u * (uint32_t)g.coutp) pc <<= 1;
         p.tmem_cols = pc;
@@ -986,6 +1031,7 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         p.nstages = ns < TC_MAX_STAGES ? ns : TC_MAX_STAGES;
         const uint32_t smem_pair = TC_SMEM_HEADER + g.act_bytes + (uint32_t)p.nstages * slab;
         p.idesc1 = idesc_base_nom | ((uint32_t)(g.coutp >> 3) << 17) | ((256u >> 4) << 24);      // M = 256 across the pair
+        p.idesc2 = idesc_base_nom | ((uint32_t)(g.N1 >> 3) << 17) | ((256u >> 4) << 24);         // stacked: N = 2*Cout
         int nsm = h->num_sms & ~1;
         int grid = 2 * p.pair_items < nsm ? 2 * p.pair_items : nsm;
         ProfScope ps(h, PROF_CONV_TC, s, flops, 0);
@@ -1152,7 +1198,7 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     for (auto &v : hres) v = 10.f * lcg(seed);
     for (auto &v : hmul) v = 1.5f * lcg(seed);
 
-    DevBuf d_in32, d_res32, d_mul32, d_in, d_res, d_mul, d_out, d_out32, d_ref32, d_wsimt, d_wtc, d_wpair;
+    DevBuf d_in32, d_res32, d_mul32, d_in, d_res, d_mul, d_out, d_out32, d_ref32, d_wsimt, d_wtc, d_wpair, d_wpair_st;
     const size_t sp_in = act_bytes(FMT_SPLIT, B, cin, H, W), sp_out = act_bytes(FMT_SPLIT, B, cout, H, W);
     if (d_in32.alloc(n_in * 4) || d_res32.alloc(n_out * 4) || d_mul32.alloc(n_out * 4) || d_in.alloc(sp_in) ||
         d_res.alloc(sp_out) || d_mul.alloc(sp_out) || d_out.alloc(sp_out) || d_out32.alloc(n_out * 4) ||
@@ -1179,6 +1225,12 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
         pack_tc_pair_weights(hw_.data(), cout, cin, ksize, ksize, cinp, coutp, bf, pp.data());
         if (d_wpair.alloc(pp.size() * 2)) return PMP_ERR_CUDA;
         PMP_CUDA(cudaMemcpy(d_wpair.p, pp.data(), pp.size() * 2, cudaMemcpyHostToDevice));
+    }
+    if (coutp == 64) {
+        std::vector<uint16_t> pp(tc_pair_stacked_elems(cinp, ksize, ksize));
+        pack_tc_pair_stacked_weights(hw_.data(), cout, cin, ksize, ksize, cinp, bf, pp.data());
+        if (d_wpair_st.alloc(pp.size() * 2)) return PMP_ERR_CUDA;
+        PMP_CUDA(cudaMemcpy(d_wpair_st.p, pp.data(), pp.size() * 2, cudaMemcpyHostToDevice));
     }
 
     auto mk = [&](void *p, int C) {
@@ -1212,15 +1264,16 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     ta.in = in; ta.out = out;
     if (flags & 2) ta.res = res;
     if (flags & 4) ta.mul = mul;
-    ta.w = (const uint16_t *)d_wtc.p; ta.w_pair = (const uint16_t *)d_wpair.p; ta.cin_pad = cinp; ta.cout_pad = coutp; ta.kh = ta.kw = ksize; ta.pad_t = ta.pad_l = ksize / 2; ta.relu = flags & 1; ta.pool = 1;
+    ta.w = (const uint16_t *)d_wtc.p; ta.w_pair = (const uint16_t *)d_wpair.p; ta.w_pair_st = (const uint16_t *)d_wpair_st.p; ta.cin_pad = cinp; ta.cout_pad = coutp; ta.kh = ta.kw = ksize; ta.pad_t = ta.pad_l = ksize / 2; ta.relu = flags & 1; ta.pool = 1;
     pmp::g_tc_scheme = ((flags >> 8) & 3) - 1;          // 0: library default, 1: unstacked, 2: stacked
     pmp::g_tc_pair = (flags >> 10) & 1 ? 1 : ((flags >> 11) & 1 ? 0 : -1);   // bit 10: CTA-pair kernel, bit 11: force single
+    pmp::g_tc_pair_st = (flags >> 12) & 1;                                    // bit 12: stacked accumulators in the pair kernel
     if (!tc_supported(cinp, coutp, ksize, ksize, H, W)) { pmp::g_tc_scheme = -1; set_error("selftest: scheme not supported"); return PMP_ERR_UNSUPPORTED; }
     rc = conv_tc(h, ta, B, s);          // warm-up (also first-launch overheads)
     cudaEventRecord(e2, s);
     if (!rc) rc = conv_tc(h, ta, B, s);
     cudaEventRecord(e3, s);
-    pmp::g_tc_scheme = -1; pmp::g_tc_pair = -1;
+    pmp::g_tc_scheme = -1; pmp::g_tc_pair = -1; pmp::g_tc_pair_st = -1;
     if (rc) return rc;
     split_to_f32_kernel<<<1024, 256, 0, s>>>(out, (float *)d_out32.p, B);
     cudaError_t ce = cudaStreamSynchronize(s);

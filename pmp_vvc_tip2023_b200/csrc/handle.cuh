@@ -13,7 +13,8 @@ struct ConvW {
     // TC engine (split precision) operand images, see pack_tc_weights / pack_tc_pair_weights in conv_tc.cu
     uint16_t *w_tc_f16 = nullptr;
     uint16_t *w_tc_bf16 = nullptr;
-    uint16_t *w_pair_f16 = nullptr, *w_pair_bf16 = nullptr;   // CTA-pair kernel images (Cout = 64 only)
+    uint16_t *w_pair_f16 = nullptr, *w_pair_bf16 = nullptr;   // CTA-pair kernel images
+    uint16_t *w_pair_st_f16 = nullptr, *w_pair_st_bf16 = nullptr;   // stacked CTA-pair images (Cout = 64 only)
     int cin_pad = 0, cout_pad = 0;      // channel counts padded to multiples of 16
 };
 

@@ -19,3 +19,22 @@ def test_tc_conv_matches_simt(cfg):
                                             ctypes.byref(t1), ctypes.byref(t2)))
     # 3-product split precision: fp16 hi/lo ~2^-22 relative, bf16 hi/lo ~2^-16
     assert me.value <= (3e-4 if fl & 8 else 2e-5) * max(am.value, 1.0), (me.value, am.value)
+
+
+# kernel / accumulator-scheme variants (flags: bit 8/9 scheme 1 unstacked 2 stacked, bit 10 CTA-pair kernel, bit 11 force the
+# single-CTA kernel, bit 12 stacked accumulators in the pair kernel), odd batches included (the pair kernel's peer CTA then
+# recomputes the last image and must drop it)
+VARIANTS = [((64, 64, 3, 32, 5, 3), 1 << 11), ((64, 64, 3, 32, 5, 3), 1 << 10), ((64, 64, 3, 32, 5, 3), (1 << 10) | (1 << 12)),
+            ((64, 64, 5, 64, 3, 1), (1 << 11) | (2 << 8)), ((64, 64, 5, 64, 3, 1), (1 << 11) | (1 << 8)),
+            ((64, 32, 3, 16, 7, 1), 1 << 10), ((64, 32, 3, 16, 7, 1), (1 << 11) | (2 << 8)), ((3, 32, 3, 16, 4, 1), 1 << 10),
+            ((32, 64, 3, 32, 3, 7), 1 << 10), ((32, 64, 5, 64, 2, 1), (1 << 10) | (1 << 12))]
+
+
+@pytest.mark.parametrize("cfg,mode", VARIANTS, ids=lambda v: str(v).replace(" ", ""))
+def test_tc_conv_variants(cfg, mode):
+    cin, cout, k, hw, b, fl = cfg
+    h = _lib.Handle.get(0)
+    me, am, t1, t2 = (ctypes.c_double() for _ in range(4))
+    _lib.check(_lib.lib().pmp_selftest_conv(h.ptr, cin, cout, k, hw, b, fl | mode, ctypes.byref(me), ctypes.byref(am),
+                                            ctypes.byref(t1), ctypes.byref(t2)))
+    assert me.value <= 2e-5 * max(am.value, 1.0), (me.value, am.value)

@@ -17,7 +17,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 VTM_SRC = "/root/reference/codec/vtm10.0-source-with-pmp-fast-alg"
-BUILD = os.path.join(ROOT, "oracle", "_ref", "vtm_build")
+BUILD = os.path.join(ROOT, "tools", "vtm_acceptance", "_build")
 INTRA_CFG = "/root/reference/codec/demo/cfg/encoder_intra_vtm.cfg"
 
 
