@@ -996,11 +996,10 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     p.idesc1 = idesc_base | ((uint32_t)(g.N1 >> 3) << 17);
     p.idesc2 = idesc_base | ((uint32_t)(g.coutp >> 3) << 17);
     p.relu = a.relu; p.stacked = g.stacked; p.pairbuf = g.pairbuf;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!h->tc_attr_set) {          // function attributes are per device: one handle per device
         PMP_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
         PMP_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
-        attr_set = true;
+        h->tc_attr_set = true;
     }
     const double flops = a.flops_override > 0 ? a.flops_override * B : 2.0 * B * H * W * (double)a.out.C * a.in.C * a.kh * a.kw;
     if (tc_pair_default() && B >= 2 && (pair_st || (a.w_pair && !g.stacked))) {

@@ -400,11 +400,10 @@ int map2partition(Handle *h, const uint8_t *qt, const float *bt, const float *di
 {
     if (B <= 0) return PMP_OK;
     PMP_CHECK_ARG(cf == 1 || cf == 2, "chroma_factor must be 1 or 2");
-    static bool attr_set = false;
     size_t smem = sizeof(WarpMaps) * DEC_WARPS;
-    if (!attr_set) {
+    if (!h->dec_attr_set) {         // function attributes are per device: one handle per device
         PMP_CUDA(cudaFuncSetAttribute(map2partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        h->dec_attr_set = true;
     }
     int grid = cdiv(B, DEC_WARPS);
     int cap = h->num_sms * 8;

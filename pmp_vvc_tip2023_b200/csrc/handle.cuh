@@ -33,6 +33,7 @@ struct Handle {
     int num_sms = 148;
     long long launches = 0;
     bool profiling = false;
+    bool tc_attr_set = false, dec_attr_set = false;     // per-device cudaFuncSetAttribute done
     ProfSlot prof[PROF_COUNT];
     std::vector<EventPair> pending;
     std::vector<cudaEvent_t> ev_pool;

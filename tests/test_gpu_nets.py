@@ -184,7 +184,8 @@ def test_cli_driver_writes_reference_files(tmp_path):
     args = Inference_QBD.build_parser().parse_args([
         "--jobID", "j1", "--inputDir", str(inp), "--outDir", str(tmp_path / "out"), "--batchSize", "5", "--startSeqID", "0",
         "--seqNum", "1", "--seqInfo", str(tmp_path / "seqs.txt"), "--cfgDir", str(cfg),
-        "--modelDir", os.path.join(ROOT, "trained_models"), "--ssRatio", "1", "--missingBD", "seeded"])
+        "--modelDir", os.path.join(ROOT, "trained_models"), "--ssRatio", "1", "--missingBD", "seeded",
+        "--gpus", str(min(2, torch.cuda.device_count()))])          # 2 GPUs: one frame each, segments concatenated
     Inference_QBD.inference_VVC_seqs(args)
     out = tmp_path / "out" / "j1" / "PartitionMat"
     names = sorted(os.listdir(out))
@@ -194,3 +195,22 @@ def test_cli_driver_writes_reference_files(tmp_path):
         want = open(os.path.join(GOLDEN, "pipeline_%s_QP32_PartitionMat.txt" % comp), "rb").read()
         assert got == want
     assert os.path.exists(tmp_path / "out" / "j1" / "Time_Sta_0_1.txt")
+
+
+@pytest.mark.parametrize("comp,qp", [("Luma", 37), ("Chroma", 22)])
+def test_bf16_split_engine_within_tolerance(comp, qp):
+    """PMP_TC_BF16 operands (hi+lo bf16, ~16 mantissa bits): still inside the 1e-2 bar (bf16x3 ~1e-3)."""
+    g = np.load(os.path.join(GOLDEN, "nets_golden.npz"))
+    h = _lib.Handle.get(0)
+    h.set_engine(_lib.ENGINE_TC, _lib.TC_BF16)
+    try:
+        x = _inputs(g, comp).cuda()
+        netq, netb = _nets(comp, qp)
+        want_qt = torch.from_numpy(g["%s_%d_qt" % (comp, qp)])
+        err_q = float((netq(x).cpu() - want_qt).abs().max())
+        outs = netb(x, want_qt.cuda())
+        want = torch.from_numpy(g["%s_%d_bd" % (comp, qp)])
+        err_b = max(float((outs[k].cpu() - want[:, k]).abs().max()) for k in range(3))
+        assert err_q <= 1e-2 and err_b <= 1e-2, (err_q, err_b)
+    finally:
+        h.set_engine(_lib.ENGINE_TC, _lib.TC_FP16)
