@@ -48,6 +48,7 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pmp_selftest_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, _P(ctypes.c_double),
                                   _P(ctypes.c_double), _P(ctypes.c_double), _P(ctypes.c_double)]),
+    "pmp_debug_tc_stalls": (c_int, [_P(ctypes.c_uint64), c_int]),
 }
 
 _lib = None

@@ -42,7 +42,7 @@ constexpr uint32_t TC_SMEM_HEADER = 1024;
 constexpr uint32_t TC_SMEM_MAX = 232448;          // 227 KB dynamic shared memory per CTA
 
 struct TcGeom {
-    int P, MT, total_mt, tiles, Rbox, groups, N1, coutp, nstages, stacked, pairbuf;
+    int P, MT, total_mt, tiles, Rbox, groups, N1, coutp, nstages, stacked, pairbuf, nbuf;
     uint32_t plane_bytes, group_bytes, act_bytes, stage_bytes, smem_bytes, tmem_cols;
 };
 
@@ -54,13 +54,31 @@ struct TcGeom {
 static int g_tc_scheme = -1;     // -1 auto, 0 unstacked, 1 stacked
 static int g_tc_pair = -1;       // -1 library default / env PMP_TC_PAIR, 0 single-CTA kernel, 1 CTA-pair kernel where applicable
 constexpr int TC_DEFAULT_PAIR = 1;
-static int g_tc_pair_st = -1;    // -1 library default / env PMP_TC_PAIR_STACKED: stacked accumulators in the pair kernel (Cout = 64)
-constexpr int TC_DEFAULT_PAIR_STACKED = 0;
 
 static bool tc_pair_default()
 {
     static const int env_pair = [] { const char *e = getenv("PMP_TC_PAIR"); return e ? atoi(e) : TC_DEFAULT_PAIR; }();
     return (g_tc_pair < 0 ? env_pair : g_tc_pair) != 0;
+}
+
+// Shared-memory split between activation buffers and the weight ring for ring stages of `slab` bytes.  Small images leave
+// room for several whole-tile activation buffers (nbuf): the producer then runs up to nbuf - 1 tiles ahead, which hides
+// the TMA latency that a single buffer per channel group exposes once per tile (the small layers are latency-bound).
+static int g_tc_nbuf_max = -1;   // -1 library default / env PMP_TC_NBUF
+static void tc_ring_layout(TcGeom &g, uint32_t slab, int taps)
+{
+    static const int env_nbuf = [] { const char *e = getenv("PMP_TC_NBUF"); return e ? atoi(e) : 4; }();
+    const int nbuf_max = g_tc_nbuf_max > 0 ? g_tc_nbuf_max : (env_nbuf > 0 ? env_nbuf : 1);
+    int want = g.groups * taps;                       // one tile's worth of slabs in flight is plenty
+    if (want > TC_MAX_STAGES) want = TC_MAX_STAGES;
+    int nb = 1;
+    while (nb < nbuf_max && (nb + 1) * g.groups <= 16 &&
+           TC_SMEM_HEADER + (uint32_t)(nb + 1) * g.act_bytes + (uint32_t)want * slab <= TC_SMEM_MAX)
+        nb++;
+    g.nbuf = nb;
+    int ns = (int)((TC_SMEM_MAX - TC_SMEM_HEADER - (uint32_t)nb * g.act_bytes) / slab);
+    g.nstages = ns < TC_MAX_STAGES ? ns : TC_MAX_STAGES;
+    g.smem_bytes = TC_SMEM_HEADER + (uint32_t)nb * g.act_bytes + (uint32_t)g.nstages * slab;
 }
 
 static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W, TcGeom &g, int scheme_override = -1)
@@ -92,11 +110,8 @@ static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W,
         uint32_t plane = (uint32_t)rbox * g.P * 16;
         uint32_t act = plane * 4 * g.groups;
         if (TC_SMEM_HEADER + act + (uint32_t)(kw + 3) * g.stage_bytes > TC_SMEM_MAX) continue;  // ring >= one filter row + 2
-        int ns = (int)((TC_SMEM_MAX - TC_SMEM_HEADER - act) / g.stage_bytes);
-        if (ns > TC_MAX_STAGES) ns = TC_MAX_STAGES;
         g.MT = mt; g.Rbox = rbox; g.plane_bytes = plane; g.group_bytes = plane * 4; g.act_bytes = act;
-        g.nstages = ns;
-        g.smem_bytes = TC_SMEM_HEADER + act + ns * g.stage_bytes;
+        tc_ring_layout(g, g.stage_bytes, kh * kw);
         g.tiles = (g.total_mt + mt - 1) / mt;
         uint32_t cols = (g.stacked && !g.pairbuf ? 16u : 8u) * g.coutp, pc = 32;
         while (pc < cols) pc <<= 1;
@@ -169,29 +184,6 @@ void pack_tc_pair_weights(const float *w, int cout, int cin, int kh, int kw, int
                         }
 }
 
-// Stacked CTA-pair operand image (Cout = 64): per CTA rank r a slab [k8 (2)][96 rows][8]:
-//   rows  0..63 : this CTA's half of the N = 128 operand [w_hi | w_lo]  (rank 0: w_hi[0..64), rank 1: w_lo[0..64))
-//   rows 64..95 : this CTA's half of the N = 64 operand w_hi            (w_hi[32r .. 32r+32))
-size_t tc_pair_stacked_elems(int cin_pad, int kh, int kw) { return (size_t)2 * (cin_pad / 16) * kh * kw * 2 * 96 * 8; }
-
-void pack_tc_pair_stacked_weights(const float *w, int cout, int cin, int kh, int kw, int cin_pad, bool bf16, uint16_t *dst)
-{
-    const int groups = cin_pad / 16, taps = kh * kw;
-    for (int r = 0; r < 2; r++)
-        for (int g = 0; g < groups; g++)
-            for (int t = 0; t < taps; t++)
-                for (int k8 = 0; k8 < 2; k8++)
-                    for (int n = 0; n < 64; n++)
-                        for (int e = 0; e < 8; e++) {
-                            const int c = g * 16 + k8 * 8 + e;
-                            uint16_t hi = 0, lo = 0;
-                            if (n < cout && c < cin) host_split(w[((size_t)n * cin + c) * taps + t], bf16, hi, lo);
-                            const size_t base = ((((size_t)r * groups + g) * taps + t) * 2 + k8) * 96 * 8;
-                            dst[base + (size_t)n * 8 + e] = r == 0 ? hi : lo;
-                            if ((n >> 5) == r) dst[base + (size_t)(64 + (n & 31)) * 8 + e] = hi;
-                        }
-}
-
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------
@@ -228,6 +220,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tma
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
+}
+// L2 prefetch of a TMA box (no shared-memory destination): issued one tile ahead so that the box load itself hits L2 --
+// per-SM TMA throughput on HBM-resident data is bounded by the requests the SM can keep in flight over the DRAM latency
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *tmap, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
@@ -290,13 +289,20 @@ struct TcParams {
     Act out, res, mul;
     int H, W, P, kh, kw, pady, padx, groups, total_mt, tiles, N1, coutp, nstages, items;
     uint32_t plane_bytes, group_bytes, stage_bytes, tmem_cols, idesc1, idesc2;
-    int relu, stacked, pairbuf;
+    int relu, stacked, pairbuf, nbuf, dbg, prefetch;
     int B, pair_items;      // CTA-pair kernel: images in the batch, work items = tiles * ceil(B/2)
     uint32_t pair_slab;     // CTA-pair kernel: bytes of one per-CTA weight slab
-    int pair_box_rows;      // CTA-pair kernel: rows of the weight tensor map covered by one slab (1 or 2)
 };
 
 struct TileGeom { int n, mt_count, q0, row0, qoff; };
+
+// Stall profile of the pair kernel (PMP_TC_DBG bit 6): cycles each role spent waiting on each barrier class, per CTA.
+// slots: 0 total (issuer 0), 1 issuer acc_empty, 2 issuer act_full, 3 issuer w_full, 4 weight producer w_empty,
+// 5 activation producer act_empty, 6 epilogue acc_full, 7 epilogue body, 8 items, 9 epilogue total
+constexpr int TC_PROF_SLOTS = 16;
+__device__ unsigned long long g_tc_stalls[160 * TC_PROF_SLOTS];
+#define TC_PROF_BEGIN(flag) long long _pt0 = (flag) ? clock64() : 0
+#define TC_PROF_END(flag, acc) do { if (flag) { long long _pt1 = clock64(); (acc) += _pt1 - _pt0; } } while (0)
 
 __device__ __forceinline__ TileGeom tile_geom(const TcParams &p, int item)
 {
@@ -432,19 +438,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-    // barrier slots: [0,8) act_full, [8,16) act_empty, [16,40) w_full, [40,64) w_empty, [64,66) acc_full per accumulator
-    // buffer, [66,74) acc_empty per accumulator (buffer, M-tile); TMEM base address at byte 1008
-    const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + 8), bar_wfull = smem_u32(bars + 16),
-                   bar_wempty = smem_u32(bars + 40), bar_acc = smem_u32(bars + 64), bar_accempty = smem_u32(bars + 66);
+    // barrier slots: [0,16) act_full and [16,32) act_empty per (activation buffer, channel group), [32,56) w_full,
+    // [56,80) w_empty, [80,82) acc_full per accumulator buffer, [82,90) acc_empty per accumulator (buffer, M-tile);
+    // TMEM base address at byte 1008
+    const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + 16), bar_wfull = smem_u32(bars + 32),
+                   bar_wempty = smem_u32(bars + 56), bar_acc = smem_u32(bars + 80), bar_accempty = smem_u32(bars + 82);
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 1008);
     uint8_t *act = smem + TC_SMEM_HEADER;
-    uint8_t *ring = act + (size_t)p.groups * p.group_bytes;
+    uint8_t *ring = act + (size_t)p.nbuf * p.groups * p.group_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int taps = p.kh * p.kw;
 
     if (threadIdx.x == 0) {
-        for (int g = 0; g < p.groups; g++) { mbar_init(bar_afull + 8 * g, 1); mbar_init(bar_aempty + 8 * g, TC_MMA_WARPS); }
+        for (int g = 0; g < p.nbuf * p.groups; g++) { mbar_init(bar_afull + 8 * g, 1); mbar_init(bar_aempty + 8 * g, TC_MMA_WARPS); }
         for (int s = 0; s < p.nstages; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, TC_MMA_WARPS); }
         mbar_init(bar_acc, p.pairbuf ? 2 : TC_MMA_WARPS);
         mbar_init(bar_acc + 8, p.pairbuf ? 2 : TC_MMA_WARPS);
@@ -480,16 +487,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== activation producer: one TMA box per 16-channel group; buffer g is refilled for the next tile as
-            //       soon as the MMAs of group g of the current tile have drained it =====
-            uint32_t idx = 0;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x, idx++) {
+            //       soon as the MMAs of group g of the current tile have drained it.
+            //       With nbuf > 1 (small images) whole tiles are loaded nbuf - 1 items ahead. =====
+            uint32_t ab = 0, aph = 0;                 // activation buffer of this item, parity of its use count
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
                 const TileGeom t = tile_geom(p, item);
+                if (p.prefetch && item + p.prefetch * (int)gridDim.x < p.items) {
+                    const TileGeom tn = tile_geom(p, item + p.prefetch * (int)gridDim.x);
+                    for (int g = 0; g < p.groups; g++) tma_prefetch_4d(&tmap, -2 * p.padx, tn.row0 - p.pady, g * 4, tn.n);
+                }
                 for (int g = 0; g < p.groups; g++) {
-                    mbar_wait_relaxed(bar_aempty + 8 * g, (idx & 1u) ^ 1u);
-                    mbar_expect_tx(bar_afull + 8 * g, p.group_bytes);
-                    tma_load_4d(smem_u32(act + (size_t)g * p.group_bytes), &tmap, bar_afull + 8 * g, -2 * p.padx,
+                    const uint32_t slot = ab * (uint32_t)p.groups + (uint32_t)g;
+                    mbar_wait_relaxed(bar_aempty + 8 * slot, aph ^ 1u);
+                    mbar_expect_tx(bar_afull + 8 * slot, p.group_bytes);
+                    tma_load_4d(smem_u32(act + (size_t)slot * p.group_bytes), &tmap, bar_afull + 8 * slot, -2 * p.padx,
                                 t.row0 - p.pady, g * 4, t.n);
                 }
+                if (++ab == (uint32_t)p.nbuf) { ab = 0; aph ^= 1u; }
             }
         }
     } else if (warp < 2 + TC_MMA_WARPS) {
@@ -504,7 +518,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
         const uint32_t group16 = p.group_bytes >> 4, stage16 = p.stage_bytes >> 4, lo16 = (2u * p.plane_bytes) >> 4;
         const uint32_t idesc = p.idesc2, idesc_st = p.idesc1, wlo16 = (uint32_t)p.coutp;        // w_lo rows follow w_hi rows
         const int KH = p.kh, K = p.kw, P = p.P, NS = p.nstages, G = p.groups;
-        uint32_t s = 0, ph = 0, idx = 0;
+        uint32_t s = 0, ph = 0, idx = 0, ab = 0, aph = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, idx++) {
             const TileGeom t = tile_geom(p, item);
             const uint32_t buf = idx & 1u;                      // tiles alternate between the two accumulator buffers
@@ -523,8 +537,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
             const uint32_t am16 = (uint32_t)mym * 128u;
             uint32_t acc = 0;
             for (int g = 0; g < G; g++) {
-                mbar_wait(bar_afull + 8 * g, idx & 1u);
-                const uint32_t ag = act16 + am16 + (uint32_t)g * group16 + (uint32_t)t.qoff;
+                const uint32_t slot = ab * (uint32_t)G + (uint32_t)g;
+                mbar_wait(bar_afull + 8 * slot, aph);
+                const uint32_t ag = act16 + am16 + slot * group16 + (uint32_t)t.qoff;
                 for (int ky = 0; ky < KH; ky++) {
                     // one filter row = K weight slabs: probe all their barriers back to back, then spin on stragglers
                     uint32_t sj[5], pj[5];
@@ -574,9 +589,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
                     __syncwarp();
                     acc = 1u;
                 }
-                if (elect_one_sync()) {                          // activation buffer g free for the next tile
-                    if (mine) umma_commit(bar_aempty + 8 * g);
-                    else mbar_arrive(bar_aempty + 8 * g);
+                if (elect_one_sync()) {                          // activation buffer free for a later tile
+                    if (mine) umma_commit(bar_aempty + 8 * slot);
+                    else mbar_arrive(bar_aempty + 8 * slot);
                 }
                 __syncwarp();
             }
@@ -585,6 +600,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
                 else mbar_arrive(bar_acc + 8 * buf);
             }
             __syncwarp();
+            if (++ab == (uint32_t)p.nbuf) { ab = 0; aph ^= 1u; }
         }
     } else {
         // ===== epilogue =====
@@ -698,7 +714,9 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, u
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// per-CTA weight slab: [2 k8][Cout/2 w_hi rows | Cout/2 w_lo rows][8] 16-bit = 32 * Cout bytes (p.pair_slab)
+// per-CTA weight slab: [2 k8][Cout/2 w_hi rows | Cout/2 w_lo rows][8] 16-bit = 32 * Cout bytes (p.pair_slab).  A ring stage
+// holds one FILTER ROW of one channel group (kw consecutive slabs, contiguous in the packed image): one full/empty barrier
+// pair, one TMA request and one commit per row instead of per tap.
 
 struct PairGeom { int n, mt_count, q0, row0, qoff; bool store; };
 
@@ -717,29 +735,115 @@ __device__ __forceinline__ PairGeom pair_geom(const TcParams &p, int item, int r
     return t;
 }
 
+struct PairBars { uint32_t afull, aempty, wfull, wempty, acc, accempty; };
+
+// MMA issuer of the leader CTA: warp 2+m owns M-tile m of BOTH CTAs' tiles (accumulator buf*4+m).  Measured
+// (tools/stall_prof.py): the issuers spent 85 % of their time executing the issue loop itself, not waiting -- ~200
+// instructions per filter row at IPC 0.1 -- so the loop is kept to the bare minimum: one barrier probe and one commit
+// per filter row (row-granular ring stages), the row's kw taps unrolled at compile time with descriptors that differ by
+// compile-time constants, every operand warp-uniform so that it lives in uniform registers.
+template <int KW>
+__device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b, uint32_t tmem_base, uint32_t act_addr,
+                                            uint32_t ring_addr, int m, int cid, int ncl, bool prof, long long t_begin)
+{
+    const uint64_t desc_c = ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);                 // SBO 128, version 1
+    const uint64_t adesc_c = desc_c | ((uint64_t)(p.plane_bytes >> 4) << 16);                    // LBO = plane stride
+    const uint64_t bdesc_c = desc_c | ((uint64_t)(p.pair_slab >> 5) << 16);                      // LBO = slab rows per k8
+    const uint32_t act16 = (act_addr >> 4) + (uint32_t)m * 128u, ring16 = ring_addr >> 4;
+    const uint32_t group16 = p.group_bytes >> 4, slab16 = p.pair_slab >> 4, row16 = (uint32_t)KW * slab16;
+    const uint64_t lo16 = (2u * p.plane_bytes) >> 4;            // a_lo planes follow the two a_hi planes
+    const uint64_t wlo16 = (uint64_t)(p.coutp >> 1);            // this CTA's w_lo rows follow its w_hi rows
+    const uint32_t idesc = p.idesc1;
+    const uint32_t peer_wempty = mapa_cluster(b.wempty, 1), peer_aempty = mapa_cluster(b.aempty, 1), peer_acc = mapa_cluster(b.acc, 1);
+    const int KH = p.kh, P = p.P, NS = p.nstages, G = p.groups;
+    long long st_a = 0, st_b = 0, st_c = 0;
+    uint32_t s = 0, ph = 0, idx = 0, ab = 0, aph = 0;
+    for (int item = cid; item < p.pair_items; item += ncl, idx++) {
+        const PairGeom t = pair_geom(p, item, 0);
+        const uint32_t buf = idx & 1u;
+        const bool mine = m < t.mt_count;
+        const uint32_t accidx = buf * 4u + (uint32_t)m;
+        const uint32_t d_tmem = tmem_base + accidx * (uint32_t)p.coutp;
+        {
+            TC_PROF_BEGIN(prof);
+            mbar_wait(b.accempty + 8 * accidx, ((idx >> 1) & 1u) ^ 1u);     // both CTAs drained it (tile idx-2)
+            TC_PROF_END(prof, st_a);
+        }
+        tc_fence_after();
+        uint32_t acc = 0;
+        for (int g = 0; g < G; g++) {
+            const uint32_t slot = ab * (uint32_t)G + (uint32_t)g;
+            { TC_PROF_BEGIN(prof); mbar_wait(b.afull + 8 * slot, aph); TC_PROF_END(prof, st_b); }
+            uint32_t arow = act16 + slot * group16 + (uint32_t)t.qoff;
+            for (int ky = 0; ky < KH; ky++, arow += (uint32_t)P) {
+                { TC_PROF_BEGIN(prof); mbar_wait(b.wfull + 8 * s, ph); TC_PROF_END(prof, st_c); }
+                tc_fence_after();
+                const uint64_t ad0 = adesc_c | (uint64_t)arow;
+                const uint64_t bd0 = bdesc_c | (uint64_t)(ring16 + s * row16);
+                if (elect_one_sync()) {
+                    if (mine) {
+#pragma unroll
+                        for (int j = 0; j < KW; j++) {
+                            const uint64_t ad = ad0 + (uint64_t)j, bd = bd0 + (uint64_t)((uint32_t)j * slab16);
+                            umma_f16_pair(d_tmem, ad, bd, idesc, j == 0 ? acc : 1u);    // a_hi * w_hi
+                            umma_f16_pair(d_tmem, ad, bd + wlo16, idesc, 1u);           // a_hi * w_lo
+                            umma_f16_pair(d_tmem, ad + lo16, bd, idesc, 1u);            // a_lo * w_hi
+                        }
+                        umma_commit_pair(b.wempty + 8 * s);                             // row free when read
+                    } else {
+                        mbar_arrive(b.wempty + 8 * s);
+                        mbar_arrive_cluster_relaxed(peer_wempty + 8 * s);
+                    }
+                }
+                __syncwarp();
+                acc = 1u;
+                if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
+            }
+            if (elect_one_sync()) {                              // activation buffer free for a later tile
+                if (mine) umma_commit_pair(b.aempty + 8 * slot);
+                else { mbar_arrive(b.aempty + 8 * slot); mbar_arrive_cluster_relaxed(peer_aempty + 8 * slot); }
+            }
+            __syncwarp();
+        }
+        if (elect_one_sync()) {                                  // accumulators of this tile complete
+            if (mine) umma_commit_pair(b.acc + 8 * buf);
+            else { mbar_arrive(b.acc + 8 * buf); mbar_arrive_cluster_relaxed(peer_acc + 8 * buf); }
+        }
+        __syncwarp();
+        if (++ab == (uint32_t)p.nbuf) { ab = 0; aph ^= 1u; }
+    }
+    if (prof && m == 0 && (threadIdx.x & 31) == 0) {
+        unsigned long long *o = g_tc_stalls + blockIdx.x * TC_PROF_SLOTS;
+        o[0] = clock64() - t_begin; o[1] = st_a; o[2] = st_b; o[3] = st_c; o[8] = idx;
+    }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-    // same barrier slots as conv_tc_kernel
-    const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + 8), bar_wfull = smem_u32(bars + 16),
-                   bar_wempty = smem_u32(bars + 40), bar_acc = smem_u32(bars + 64), bar_accempty = smem_u32(bars + 66);
+    // same barrier slots as conv_tc_kernel; a weight stage is a filter row here
+    PairBars b;
+    b.afull = smem_u32(bars); b.aempty = smem_u32(bars + 16); b.wfull = smem_u32(bars + 32);
+    b.wempty = smem_u32(bars + 56); b.acc = smem_u32(bars + 80); b.accempty = smem_u32(bars + 82);
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 1008);
     uint8_t *act = smem + TC_SMEM_HEADER;
-    uint8_t *ring = act + (size_t)p.groups * p.group_bytes;
+    uint8_t *ring = act + (size_t)p.nbuf * p.groups * p.group_bytes;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
-    const int taps = p.kh * p.kw;
+    const bool prof = (p.dbg & 64) != 0;
+    const long long t_begin = prof ? clock64() : 0;
 
     if (threadIdx.x == 0) {
-        for (int g = 0; g < p.groups; g++) { mbar_init(bar_afull + 8 * g, 1); mbar_init(bar_aempty + 8 * g, TC_MMA_WARPS); }
-        for (int s = 0; s < p.nstages; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, TC_MMA_WARPS); }
-        mbar_init(bar_acc, p.pairbuf ? 2 : TC_MMA_WARPS);
-        mbar_init(bar_acc + 8, p.pairbuf ? 2 : TC_MMA_WARPS);
-        for (int m = 0; m < 8; m++) mbar_init(bar_accempty + 8 * m, 2 * TC_EPI_WARPS);
+        for (int g = 0; g < p.nbuf * p.groups; g++) { mbar_init(b.afull + 8 * g, 1); mbar_init(b.aempty + 8 * g, TC_MMA_WARPS); }
+        for (int s = 0; s < p.nstages; s++) { mbar_init(b.wfull + 8 * s, 1); mbar_init(b.wempty + 8 * s, TC_MMA_WARPS); }
+        mbar_init(b.acc, TC_MMA_WARPS);
+        mbar_init(b.acc + 8, TC_MMA_WARPS);
+        for (int m = 0; m < 8; m++) mbar_init(b.accempty + 8 * m, 2 * TC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -754,133 +858,56 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
 
     if (warp == 0) {
         if (lane == 0) {
-            // ===== weight producer: this CTA's half of every (group, tap) slab; bytes are counted on the leader =====
-            const int per_item = taps * p.groups;
-            const uint32_t lead_wfull = mapa_cluster(bar_wfull, 0);
+            // ===== weight producer: this CTA's half of every (group, filter row) stage; bytes are counted on the leader =====
+            const int rows_per_item = p.kh * p.groups;
+            const uint32_t row_bytes = (uint32_t)p.kw * p.pair_slab;
+            const uint32_t lead_wfull = mapa_cluster(b.wfull, 0);
+            const int slab0 = (int)rank * rows_per_item * p.kw;
+            long long st = 0;
             uint32_t s = 0, ph = 0;
             for (int item = cid; item < p.pair_items; item += ncl) {
-                for (int it = 0; it < per_item; it++) {
-                    mbar_wait_relaxed(bar_wempty + 8 * s, ph ^ 1u);
-                    if (rank == 0) mbar_expect_tx(bar_wfull + 8 * s, 2u * p.pair_slab);
-                    tma_load_2d_pair(smem_u32(ring) + s * p.pair_slab, &tmap_w, lead_wfull + 8 * s, 0,
-                                     ((int)rank * per_item + it) * p.pair_box_rows);
+                for (int it = 0; it < rows_per_item; it++) {
+                    { TC_PROF_BEGIN(prof); mbar_wait_relaxed(b.wempty + 8 * s, ph ^ 1u); TC_PROF_END(prof, st); }
+                    if (rank == 0) mbar_expect_tx(b.wfull + 8 * s, 2u * row_bytes);
+                    tma_load_2d_pair(smem_u32(ring) + s * row_bytes, &tmap_w, lead_wfull + 8 * s, 0, slab0 + it * p.kw);
                     if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1u; }
                 }
             }
+            if (prof) g_tc_stalls[blockIdx.x * TC_PROF_SLOTS + 4] = st;
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== activation producer (own image), bytes counted on the leader's act_full =====
-            const uint32_t lead_afull = mapa_cluster(bar_afull, 0);
-            uint32_t idx = 0;
-            for (int item = cid; item < p.pair_items; item += ncl, idx++) {
+            const uint32_t lead_afull = mapa_cluster(b.afull, 0);
+            long long st = 0;
+            uint32_t ab = 0, aph = 0;
+            for (int item = cid; item < p.pair_items; item += ncl) {
                 const PairGeom t = pair_geom(p, item, (int)rank);
                 for (int g = 0; g < p.groups; g++) {
-                    mbar_wait_relaxed(bar_aempty + 8 * g, (idx & 1u) ^ 1u);
-                    if (rank == 0) mbar_expect_tx(bar_afull + 8 * g, 2u * p.group_bytes);
-                    tma_load_4d_pair(smem_u32(act + (size_t)g * p.group_bytes), &tmap, lead_afull + 8 * g, -2 * p.padx,
+                    const uint32_t slot = ab * (uint32_t)p.groups + (uint32_t)g;
+                    { TC_PROF_BEGIN(prof); mbar_wait_relaxed(b.aempty + 8 * slot, aph ^ 1u); TC_PROF_END(prof, st); }
+                    if (rank == 0) mbar_expect_tx(b.afull + 8 * slot, 2u * p.group_bytes);
+                    tma_load_4d_pair(smem_u32(act + (size_t)slot * p.group_bytes), &tmap, lead_afull + 8 * slot, -2 * p.padx,
                                      t.row0 - p.pady, g * 4, t.n);
                 }
+                if (++ab == (uint32_t)p.nbuf) { ab = 0; aph ^= 1u; }
             }
+            if (prof) g_tc_stalls[blockIdx.x * TC_PROF_SLOTS + 5] = st;
         }
     } else if (warp < 2 + TC_MMA_WARPS) {
         if (rank == 0) {
-            // ===== MMA issuers (leader only).  Default: warp 2+m owns M-tile m of BOTH CTAs' tiles (accumulator buf*4+m).
-            //       pairbuf (stacked, Cout = 64): tiles have 2 M-tiles; warp 2+m owns M-tile m&1 of the tiles whose
-            //       accumulator buffer is m>>1, the other two issuers only walk the barriers. =====
+            // ===== MMA issuers (leader only) =====
             const int m = warp - 2;
-            const int mym = p.pairbuf ? (m & 1) : m;
-            const uint64_t desc_c = ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);
-            const uint64_t adesc_c = desc_c | ((uint64_t)(p.plane_bytes >> 4) << 16);
-            const uint64_t bdesc_c = desc_c | ((uint64_t)(p.pair_slab >> 5) << 16);              // LBO = slab rows per k8 (16 B each)
-            const uint32_t act16 = (smem_u32(act) >> 4) + (uint32_t)mym * 128u, ring16 = smem_u32(ring) >> 4;
-            const uint32_t group16 = p.group_bytes >> 4, stage16 = p.pair_slab >> 4, lo16 = (2u * p.plane_bytes) >> 4;
-            const uint32_t idesc = p.idesc1, idesc_st = p.idesc2;
-            const uint32_t wlo16 = (uint32_t)p.coutp >> 1;      // unstacked: this CTA's w_lo rows follow its w_hi rows
-            const uint32_t b2_16 = (uint32_t)p.coutp;           // stacked: rows of the N = Cout operand follow the N = 2*Cout half
-            const int KH = p.kh, K = p.kw, P = p.P, NS = p.nstages, G = p.groups;
-            uint32_t s = 0, ph = 0, idx = 0;
-            for (int item = cid; item < p.pair_items; item += ncl, idx++) {
-                const PairGeom t = pair_geom(p, item, 0);
-                const uint32_t buf = idx & 1u;
-                const bool owner = !p.pairbuf || (uint32_t)(m >> 1) == buf;
-                const bool mine = owner && mym < t.mt_count;
-                const uint32_t accidx = p.pairbuf ? (uint32_t)m : buf * 4u + (uint32_t)m;
-                const uint32_t d_tmem = tmem_base + accidx * (uint32_t)(p.stacked ? p.N1 : p.coutp);
-                if (owner) {
-                    mbar_wait(bar_accempty + 8 * accidx, ((idx >> 1) & 1u) ^ 1u);   // both CTAs drained it (tile idx-2)
-                    tc_fence_after();
-                }
-                uint32_t acc = 0;
-                for (int g = 0; g < G; g++) {
-                    mbar_wait(bar_afull + 8 * g, idx & 1u);
-                    const uint32_t ag = act16 + (uint32_t)g * group16 + (uint32_t)t.qoff;
-                    for (int ky = 0; ky < KH; ky++) {
-                        uint32_t sj[5], pj[5];
-                        bool ok[5];
-                        {
-                            uint32_t s2 = s, ph2 = ph;
-#pragma unroll
-                            for (int j = 0; j < 5; j++) {
-                                if (j < K) {
-                                    sj[j] = s2; pj[j] = ph2;
-                                    ok[j] = mbar_try_wait(bar_wfull + 8 * s2, ph2);
-                                    if (++s2 == (uint32_t)NS) { s2 = 0; ph2 ^= 1u; }
-                                }
-                            }
-                            s = s2; ph = ph2;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 5; j++)
-                            if (j < K) while (!ok[j]) ok[j] = mbar_try_wait(bar_wfull + 8 * sj[j], pj[j]);
-                        tc_fence_after();
-                        if (elect_one_sync()) {
-                            if (mine) {
-                                const uint64_t ad0 = adesc_c | (uint64_t)(ag + (uint32_t)(ky * P));
-#pragma unroll
-                                for (int j = 0; j < 5; j++) {
-                                    if (j < K) {
-                                        const uint64_t ad = ad0 + (uint64_t)j;
-                                        const uint64_t bd = bdesc_c | (uint64_t)(ring16 + sj[j] * stage16);
-                                        if (p.stacked) {
-                                            umma_f16_pair(d_tmem, ad, bd, idesc_st, acc);                               // a_hi * [w_hi | w_lo]
-                                            umma_f16_pair(d_tmem, ad + (uint64_t)lo16, bd + (uint64_t)b2_16, idesc, 1u);  // a_lo * w_hi
-                                        } else {
-                                            umma_f16_pair(d_tmem, ad, bd, idesc, acc);                      // a_hi * w_hi
-                                            umma_f16_pair(d_tmem, ad, bd + (uint64_t)wlo16, idesc, 1u);     // a_hi * w_lo
-                                            umma_f16_pair(d_tmem, ad + (uint64_t)lo16, bd, idesc, 1u);      // a_lo * w_hi
-                                        }
-                                        umma_commit_pair(bar_wempty + 8 * sj[j]);
-                                        acc = 1u;
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 5; j++)
-                                    if (j < K) { mbar_arrive(bar_wempty + 8 * sj[j]); mbar_arrive_cluster_relaxed(mapa_cluster(bar_wempty + 8 * sj[j], 1)); }
-                            }
-                        }
-                        __syncwarp();
-                        acc = 1u;
-                    }
-                    if (elect_one_sync()) {
-                        if (mine) umma_commit_pair(bar_aempty + 8 * g);
-                        else { mbar_arrive(bar_aempty + 8 * g); mbar_arrive_cluster_relaxed(mapa_cluster(bar_aempty + 8 * g, 1)); }
-                    }
-                    __syncwarp();
-                }
-                if (owner && elect_one_sync()) {
-                    if (mine) umma_commit_pair(bar_acc + 8 * buf);
-                    else { mbar_arrive(bar_acc + 8 * buf); mbar_arrive_cluster_relaxed(mapa_cluster(bar_acc + 8 * buf, 1)); }
-                }
-                __syncwarp();
-            }
+            if (p.kw == 3) pair_issuer<3>(p, b, tmem_base, smem_u32(act), smem_u32(ring), m, cid, ncl, prof, t_begin);
+            else if (p.kw == 5) pair_issuer<5>(p, b, tmem_base, smem_u32(act), smem_u32(ring), m, cid, ncl, prof, t_begin);
+            else pair_issuer<1>(p, b, tmem_base, smem_u32(act), smem_u32(ring), m, cid, ncl, prof, t_begin);
         }
     } else {
         // ===== epilogue (both CTAs, own accumulators; the drain is reported to the leader) =====
         const int quarter = warp & 3, half = (warp - 2 - TC_MMA_WARPS) >> 2;
         const int nchunk = p.coutp >> 3, chh = nchunk >> 1, ch0 = half * chh;
-        const uint32_t lead_accempty = mapa_cluster(bar_accempty, 0);
+        const uint32_t lead_accempty = mapa_cluster(b.accempty, 0);
+        long long st = 0;
         uint32_t idx = 0;
         for (int item = cid; item < p.pair_items; item += ncl, idx++) {
             const PairGeom t = pair_geom(p, item, (int)rank);
@@ -899,16 +926,15 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 }
             }
             const uint32_t buf = idx & 1u;
-            mbar_wait_relaxed(bar_acc + 8 * buf, (idx >> 1) & 1u);
+            { TC_PROF_BEGIN(prof); mbar_wait_relaxed(b.acc + 8 * buf, (idx >> 1) & 1u); TC_PROF_END(prof, st); }
             tc_fence_after();
-            const int nmt = p.pairbuf ? 2 : 4;
-            for (int mt = 0; mt < nmt; mt++) {
-                const uint32_t accidx = (uint32_t)nmt * buf + (uint32_t)mt;
+            for (int mt = 0; mt < 4; mt++) {
+                const uint32_t accidx = 4u * buf + (uint32_t)mt;
                 if (mt < t.mt_count) {
                     const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
                     const int r = pos / p.P, c = pos - r * p.P;
                     const bool valid = t.store && (c < p.W) && (r < p.H);
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + accidx * (uint32_t)(p.stacked ? p.N1 : p.coutp);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + accidx * (uint32_t)p.coutp;
                     if (chh == 4) epilogue_chunks<4>(p, taddr, ch0, t.n, r, c, valid);
                     else
                         for (int j = 0; j < chh; j++) epilogue_chunks<1>(p, taddr, ch0 + j, t.n, r, c, valid);
@@ -916,10 +942,14 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 }
                 __syncwarp();
                 if (lane == 0) {        // TMEM reads are complete (wait::ld); nothing else needs ordering with this arrival
-                    if (rank == 0) mbar_arrive(bar_accempty + 8 * accidx);
+                    if (rank == 0) mbar_arrive(b.accempty + 8 * accidx);
                     else mbar_arrive_cluster_relaxed(lead_accempty + 8 * accidx);
                 }
             }
+        }
+        if (prof && lane == 0 && warp == 2 + TC_MMA_WARPS) {
+            unsigned long long *o = g_tc_stalls + blockIdx.x * TC_PROF_SLOTS;
+            o[6] = st; o[9] = clock64() - t_begin;
         }
     }
     tc_fence_before();
@@ -957,10 +987,7 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     if (B <= 0) return PMP_OK;
     TcGeom g;
     const int H = a.Ho ? a.Ho : a.in.H, W = a.in.W, Hin = a.in.H;
-    // CTA-pair kernel with stacked accumulators (Cout = 64): 2-M-tile tiles, geometry of the stacked/pairbuf scheme
-    static const int env_pair_st = [] { const char *e = getenv("PMP_TC_PAIR_STACKED"); return e ? atoi(e) : TC_DEFAULT_PAIR_STACKED; }();
-    const bool pair_st = tc_pair_default() && (g_tc_pair_st < 0 ? env_pair_st : g_tc_pair_st) && a.w_pair_st && a.cout_pad == 64 && B >= 2;
-    if (a.in.fmt != FMT_SPLIT || a.out.fmt != FMT_SPLIT || !tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g, pair_st ? 1 : -1) ||
+    if (a.in.fmt != FMT_SPLIT || a.out.fmt != FMT_SPLIT || !tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g) ||
         a.in.Cp != a.cin_pad || a.out.Cp != a.cout_pad || a.pool != 1 || a.out.H != H || a.out.W != W) {
         set_error("conv_tc: unsupported configuration cin %d cout %d k %dx%d %dx%d", a.cin_pad, a.cout_pad, a.kh, a.kw, H, W);
         return PMP_ERR_UNSUPPORTED;
@@ -995,24 +1022,28 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     const uint32_t idesc_base = idesc_base_nom | ((128u >> 4) << 24);
     p.idesc1 = idesc_base | ((uint32_t)(g.N1 >> 3) << 17);
     p.idesc2 = idesc_base | ((uint32_t)(g.coutp >> 3) << 17);
-    p.relu = a.relu; p.stacked = g.stacked; p.pairbuf = g.pairbuf;
+    p.relu = a.relu; p.stacked = g.stacked; p.pairbuf = g.pairbuf; p.nbuf = g.nbuf;
+    static const int env_dbg = [] { const char *e = getenv("PMP_TC_DBG"); return e ? atoi(e) : 0; }();   // timing experiments only
+    p.dbg = env_dbg;
+    static const int env_pf = [] { const char *e = getenv("PMP_TC_PREFETCH"); return e ? atoi(e) : 1; }();   // tiles of L2 prefetch distance
+    p.prefetch = env_pf;
     if (!h->tc_attr_set) {          // function attributes are per device: one handle per device
         PMP_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
         PMP_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
         h->tc_attr_set = true;
     }
     const double flops = a.flops_override > 0 ? a.flops_override * B : 2.0 * B * H * W * (double)a.out.C * a.in.C * a.kh * a.kw;
-    if (tc_pair_default() && B >= 2 && (pair_st || (a.w_pair && !g.stacked))) {
-        // CTA-pair kernel: 2-D tensor map over this conv's per-CTA weight slabs (8-byte elements, <= 256 per box row)
+    if (tc_pair_default() && B >= 2 && a.w_pair && !g.stacked) {
+        // CTA-pair kernel: 2-D tensor map over this conv's per-CTA weight slabs (8-byte elements, one slab per map row);
+        // one box = one filter row of one channel group = kw consecutive slabs = one ring stage
         CUtensorMap tmap_w;
         const cuuint64_t nslab = (cuuint64_t)2 * g.groups * a.kh * a.kw;
-        const uint32_t slab = pair_st ? 3072u : 32u * (uint32_t)g.coutp;
-        const uint32_t box_rows = slab / 8 > 256 ? 2u : 1u, row_bytes = slab / box_rows;
-        cuuint64_t wdim[2] = {row_bytes / 8, nslab * box_rows};
-        cuuint64_t wstr[1] = {row_bytes};
-        cuuint32_t wbox[2] = {row_bytes / 8, box_rows};
+        const uint32_t slab = 32u * (uint32_t)g.coutp;                   // <= 2 KB = 256 elements
+        cuuint64_t wdim[2] = {slab / 8, nslab};
+        cuuint64_t wstr[1] = {slab};
+        cuuint32_t wbox[2] = {slab / 8, (cuuint32_t)a.kw};
         cuuint32_t west[2] = {1, 1};
-        cr = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void *)(pair_st ? a.w_pair_st : a.w_pair), wdim, wstr, wbox, west,
+        cr = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void *)a.w_pair, wdim, wstr, wbox, west,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) {
@@ -1021,16 +1052,14 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         }
         p.B = B;
         p.pair_items = g.tiles * ((B + 1) / 2);
-        // unstacked: 4 M-tiles x 2 buffers x Cout columns; stacked (Cout = 64): 2 M-tiles x 2 buffers x 2*Cout columns
-        p.stacked = pair_st ? 1 : 0; p.pairbuf = pair_st ? 1 : 0; p.pair_slab = slab; p.pair_box_rows = (int)box_rows;
+        p.stacked = 0; p.pairbuf = 0; p.pair_slab = slab;
         uint32_t pc = 32;
-        while (pc < 8u * (uint32_t)g.coutp) pc <<= 1;
+        while (pc < 8u * (uint32_t)g.coutp) pc <<= 1;           // 4 M-tiles x 2 buffers x Cout columns
         p.tmem_cols = pc;
-        int ns = (int)((TC_SMEM_MAX - TC_SMEM_HEADER - g.act_bytes) / slab);
-        p.nstages = ns < TC_MAX_STAGES ? ns : TC_MAX_STAGES;
-        const uint32_t smem_pair = TC_SMEM_HEADER + g.act_bytes + (uint32_t)p.nstages * slab;
+        tc_ring_layout(g, slab * (uint32_t)a.kw, a.kh);           // ring stages are filter rows
+        p.nstages = g.nstages; p.nbuf = g.nbuf;
+        const uint32_t smem_pair = g.smem_bytes;
         p.idesc1 = idesc_base_nom | ((uint32_t)(g.coutp >> 3) << 17) | ((256u >> 4) << 24);      // M = 256 across the pair
-        p.idesc2 = idesc_base_nom | ((uint32_t)(g.N1 >> 3) << 17) | ((256u >> 4) << 24);         // stacked: N = 2*Cout
         int nsm = h->num_sms & ~1;
         int grid = 2 * p.pair_items < nsm ? 2 * p.pair_items : nsm;
         ProfScope ps(h, PROF_CONV_TC, s, flops, 0);
@@ -1174,7 +1203,15 @@ float lcg(uint32_t &s)
 
 struct pmp_handle : public pmp::Handle {};
 
-// flags: bit0 relu, bit1 identity residual, bit2 attention product, bit3 bf16 operands, bits 8..15 descriptor variant,
+// Debug: copy the pair kernel's per-CTA stall counters (PMP_TC_DBG bit 6) to the host; n = number of uint64 wanted.
+extern "C" int pmp_debug_tc_stalls(unsigned long long *out, int n)
+{
+    if (!out || n <= 0 || n > 160 * pmp::TC_PROF_SLOTS) return PMP_ERR_ARG;
+    PMP_CUDA(cudaMemcpyFromSymbol(out, pmp::g_tc_stalls, (size_t)n * sizeof(unsigned long long)));
+    return PMP_OK;
+}
+
+// flags: bit0 relu, bit1 identity residual, bit2 attention product, bit3 bf16 operands, bits 8..15 kernel variant,
 // bit 16: verbose mismatch report on stderr
 extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, int hw, int batch, int flags, double *max_err,
                                  double *ref_absmax, double *ms_tc, double *ms_simt)
@@ -1190,14 +1227,17 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     }
     uint32_t seed = 12345u + cin * 7 + cout * 13 + ksize * 31 + hw;
     const size_t n_in = (size_t)B * cin * H * W, n_out = (size_t)B * cout * H * W, n_w = (size_t)cout * cin * ksize * ksize;
-    std::vector<float> hin(n_in), hw_(n_w), hres(n_out), hmul(n_out);
+    // host data for at most 8 distinct images; larger batches (timing runs) repeat them on the device
+    const int Bu = B < 8 ? B : 8;
+    const size_t u_in = (size_t)Bu * cin * H * W, u_out = (size_t)Bu * cout * H * W;
+    std::vector<float> hin(u_in), hw_(n_w), hres(u_out), hmul(u_out);
     for (auto &v : hin) v = 40.f * fabsf(lcg(seed)) * (lcg(seed) > -0.3f ? 1.f : 0.f);     // relu-like activations
     const float wb = sqrtf(3.0f / (cin * ksize * ksize));
     for (auto &v : hw_) v = wb * lcg(seed);
     for (auto &v : hres) v = 10.f * lcg(seed);
     for (auto &v : hmul) v = 1.5f * lcg(seed);
 
-    DevBuf d_in32, d_res32, d_mul32, d_in, d_res, d_mul, d_out, d_out32, d_ref32, d_wsimt, d_wtc, d_wpair, d_wpair_st;
+    DevBuf d_in32, d_res32, d_mul32, d_in, d_res, d_mul, d_out, d_out32, d_ref32, d_wsimt, d_wtc, d_wpair;
     const size_t sp_in = act_bytes(FMT_SPLIT, B, cin, H, W), sp_out = act_bytes(FMT_SPLIT, B, cout, H, W);
     if (d_in32.alloc(n_in * 4) || d_res32.alloc(n_out * 4) || d_mul32.alloc(n_out * 4) || d_in.alloc(sp_in) ||
         d_res.alloc(sp_out) || d_mul.alloc(sp_out) || d_out.alloc(sp_out) || d_out32.alloc(n_out * 4) ||
@@ -1205,9 +1245,18 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
         set_error("selftest: cudaMalloc failed");
         return PMP_ERR_CUDA;
     }
-    PMP_CUDA(cudaMemcpy(d_in32.p, hin.data(), n_in * 4, cudaMemcpyHostToDevice));
-    PMP_CUDA(cudaMemcpy(d_res32.p, hres.data(), n_out * 4, cudaMemcpyHostToDevice));
-    PMP_CUDA(cudaMemcpy(d_mul32.p, hmul.data(), n_out * 4, cudaMemcpyHostToDevice));
+    auto upload_tiled = [&](void *dst, const std::vector<float> &src, size_t total) -> cudaError_t {
+        cudaError_t e = cudaMemcpy(dst, src.data(), src.size() * 4, cudaMemcpyHostToDevice);
+        for (size_t filled = src.size(); e == cudaSuccess && filled < total;) {
+            const size_t n = filled < total - filled ? filled : total - filled;
+            e = cudaMemcpy((float *)dst + filled, dst, n * 4, cudaMemcpyDeviceToDevice);
+            filled += n;
+        }
+        return e;
+    };
+    PMP_CUDA(upload_tiled(d_in32.p, hin, n_in));
+    PMP_CUDA(upload_tiled(d_res32.p, hres, n_out));
+    PMP_CUDA(upload_tiled(d_mul32.p, hmul, n_out));
     // weights: SIMT layout + TC packing
     const int coutw = (cout + 3) & ~3, taps = ksize * ksize;
     std::vector<float> ps((size_t)cin * taps * coutw, 0.f);
@@ -1224,12 +1273,6 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
         pack_tc_pair_weights(hw_.data(), cout, cin, ksize, ksize, cinp, coutp, bf, pp.data());
         if (d_wpair.alloc(pp.size() * 2)) return PMP_ERR_CUDA;
         PMP_CUDA(cudaMemcpy(d_wpair.p, pp.data(), pp.size() * 2, cudaMemcpyHostToDevice));
-    }
-    if (coutp == 64) {
-        std::vector<uint16_t> pp(tc_pair_stacked_elems(cinp, ksize, ksize));
-        pack_tc_pair_stacked_weights(hw_.data(), cout, cin, ksize, ksize, cinp, bf, pp.data());
-        if (d_wpair_st.alloc(pp.size() * 2)) return PMP_ERR_CUDA;
-        PMP_CUDA(cudaMemcpy(d_wpair_st.p, pp.data(), pp.size() * 2, cudaMemcpyHostToDevice));
     }
 
     auto mk = [&](void *p, int C) {
@@ -1263,16 +1306,16 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     ta.in = in; ta.out = out;
     if (flags & 2) ta.res = res;
     if (flags & 4) ta.mul = mul;
-    ta.w = (const uint16_t *)d_wtc.p; ta.w_pair = (const uint16_t *)d_wpair.p; ta.w_pair_st = (const uint16_t *)d_wpair_st.p; ta.cin_pad = cinp; ta.cout_pad = coutp; ta.kh = ta.kw = ksize; ta.pad_t = ta.pad_l = ksize / 2; ta.relu = flags & 1; ta.pool = 1;
+    ta.w = (const uint16_t *)d_wtc.p; ta.w_pair = (const uint16_t *)d_wpair.p; ta.cin_pad = cinp; ta.cout_pad = coutp; ta.kh = ta.kw = ksize; ta.pad_t = ta.pad_l = ksize / 2; ta.relu = flags & 1; ta.pool = 1;
     pmp::g_tc_scheme = ((flags >> 8) & 3) - 1;          // 0: library default, 1: unstacked, 2: stacked
     pmp::g_tc_pair = (flags >> 10) & 1 ? 1 : ((flags >> 11) & 1 ? 0 : -1);   // bit 10: CTA-pair kernel, bit 11: force single
-    pmp::g_tc_pair_st = (flags >> 12) & 1;                                    // bit 12: stacked accumulators in the pair kernel
+    pmp::g_tc_nbuf_max = ((flags >> 13) & 7) ? ((flags >> 13) & 7) : -1;      // bits 13..15: cap on activation buffers (0: default)
     if (!tc_supported(cinp, coutp, ksize, ksize, H, W)) { pmp::g_tc_scheme = -1; set_error("selftest: scheme not supported"); return PMP_ERR_UNSUPPORTED; }
     rc = conv_tc(h, ta, B, s);          // warm-up (also first-launch overheads)
     cudaEventRecord(e2, s);
     if (!rc) rc = conv_tc(h, ta, B, s);
     cudaEventRecord(e3, s);
-    pmp::g_tc_scheme = -1; pmp::g_tc_pair = -1; pmp::g_tc_pair_st = -1;
+    pmp::g_tc_scheme = -1; pmp::g_tc_pair = -1; pmp::g_tc_nbuf_max = -1;
     if (rc) return rc;
     split_to_f32_kernel<<<1024, 256, 0, s>>>(out, (float *)d_out32.p, B);
     cudaError_t ce = cudaStreamSynchronize(s);

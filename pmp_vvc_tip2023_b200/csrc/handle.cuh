@@ -14,7 +14,6 @@ struct ConvW {
     uint16_t *w_tc_f16 = nullptr;
     uint16_t *w_tc_bf16 = nullptr;
     uint16_t *w_pair_f16 = nullptr, *w_pair_bf16 = nullptr;   // CTA-pair kernel images
-    uint16_t *w_pair_st_f16 = nullptr, *w_pair_st_bf16 = nullptr;   // stacked CTA-pair images (Cout = 64 only)
     int cin_pad = 0, cout_pad = 0;      // channel counts padded to multiples of 16
 };
 

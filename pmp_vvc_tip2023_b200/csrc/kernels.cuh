@@ -33,7 +33,6 @@ struct TcConvArgs {
     Act mul;                // optional attention product (FMT_SPLIT, shape of the stored output)
     const uint16_t *w = nullptr;    // packed main weights (see pack_tc_weights)
     const uint16_t *w_pair = nullptr;   // CTA-pair operand image or nullptr
-    const uint16_t *w_pair_st = nullptr;    // stacked CTA-pair operand image (Cout = 64) or nullptr
     const float *bias = nullptr;    // [cout_pad] fp32 or nullptr (stems only)
     int cin_pad = 0, cout_pad = 0, kh = 1, kw = 1;
     int pad_t = 0, pad_l = 0;       // input coordinate = output coordinate + tap - pad
@@ -47,8 +46,6 @@ bool tc_supported(int cin_pad, int cout_pad, int kh, int kw, int H, int W);
 size_t tc_packed_elems(int cin_pad, int cout_pad, int kh, int kw);
 void pack_tc_weights(const float *w, int cout, int cin, int kh, int kw, int cin_pad, int cout_pad, bool bf16, uint16_t *dst);
 size_t tc_pair_packed_elems(int cin_pad, int cout_pad, int kh, int kw);
-size_t tc_pair_stacked_elems(int cin_pad, int kh, int kw);
-void pack_tc_pair_stacked_weights(const float *w, int cout, int cin, int kh, int kw, int cin_pad, bool bf16, uint16_t *dst);
 void pack_tc_pair_weights(const float *w, int cout, int cin, int kh, int kw, int cin_pad, int cout_pad, bool bf16, uint16_t *dst);
 // U[c*kw + j][y][x] = X[c][y][x + j] (x2 = cat[x, pad_lu(up(qt))] when qt != nullptr): the kx taps of a first-layer conv
 // unrolled into channels so that the tensor-core kernel can run it as a kh x 1 conv.  out: FMT_SPLIT [B, (cx+1?)*kw, S0, S1]

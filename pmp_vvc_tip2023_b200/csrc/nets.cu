@@ -198,14 +198,6 @@ int weights_create(Handle *h, int net, const float *const *tensors, const int64_
                 pack_tc_pair_weights(tensors[i], co, ci, kh, kw, cw.cin_pad, cw.cout_pad, true, pp.data());
                 rc = dev_upload(ws, pp, &cw.w_pair_bf16);
             }
-            if (!rc && cw.cout_pad == 64) {
-                std::vector<uint16_t> ps2(tc_pair_stacked_elems(cw.cin_pad, kh, kw));
-                pack_tc_pair_stacked_weights(tensors[i], co, ci, kh, kw, cw.cin_pad, false, ps2.data());
-                rc = dev_upload(ws, ps2, &cw.w_pair_st_f16);
-                if (rc) break;
-                pack_tc_pair_stacked_weights(tensors[i], co, ci, kh, kw, cw.cin_pad, true, ps2.data());
-                rc = dev_upload(ws, ps2, &cw.w_pair_st_bf16);
-            }
         }
     }
     if (rc == PMP_OK) rc = build_stem_tc(ws, net, spec, tensors);
@@ -294,7 +286,6 @@ struct Net {
             a.in = in; a.res = o.res; a.mul = o.mul;
             a.w = in.bf16 ? w->w_tc_bf16 : w->w_tc_f16;
             a.w_pair = in.bf16 ? w->w_pair_bf16 : w->w_pair_f16;
-            a.w_pair_st = in.bf16 ? w->w_pair_st_bf16 : w->w_pair_st_f16;
             a.cin_pad = w->cin_pad; a.cout_pad = w->cout_pad; a.kh = w->kh; a.kw = w->kw; a.pad_t = pad_t; a.pad_l = pad_l;
             a.relu = o.relu; a.pool = 1;
             if (o.pool == 2) {

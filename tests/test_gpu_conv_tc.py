@@ -22,12 +22,14 @@ def test_tc_conv_matches_simt(cfg):
 
 
 # kernel / accumulator-scheme variants (flags: bit 8/9 scheme 1 unstacked 2 stacked, bit 10 CTA-pair kernel, bit 11 force the
-# single-CTA kernel, bit 12 stacked accumulators in the pair kernel), odd batches included (the pair kernel's peer CTA then
-# recomputes the last image and must drop it)
-VARIANTS = [((64, 64, 3, 32, 5, 3), 1 << 11), ((64, 64, 3, 32, 5, 3), 1 << 10), ((64, 64, 3, 32, 5, 3), (1 << 10) | (1 << 12)),
+# single-CTA kernel, bits 13..15 cap on the activation buffers), odd batches included (the pair kernel's peer CTA then
+# recomputes the last image and must drop it), batches large enough for several tiles per cluster (ring wrap-around)
+VARIANTS = [((64, 64, 3, 32, 5, 3), 1 << 11), ((64, 64, 3, 32, 5, 3), 1 << 10), ((64, 64, 3, 32, 5, 3), (1 << 10) | (1 << 13)),
             ((64, 64, 5, 64, 3, 1), (1 << 11) | (2 << 8)), ((64, 64, 5, 64, 3, 1), (1 << 11) | (1 << 8)),
             ((64, 32, 3, 16, 7, 1), 1 << 10), ((64, 32, 3, 16, 7, 1), (1 << 11) | (2 << 8)), ((3, 32, 3, 16, 4, 1), 1 << 10),
-            ((32, 64, 3, 32, 3, 7), 1 << 10), ((32, 64, 5, 64, 2, 1), (1 << 10) | (1 << 12))]
+            ((32, 64, 3, 32, 3, 7), 1 << 10), ((32, 64, 5, 64, 2, 1), 1 << 10), ((64, 64, 5, 64, 5, 3), 1 << 10),
+            ((32, 16, 3, 16, 9, 3), 1 << 10), ((32, 16, 3, 16, 9, 3), (1 << 10) | (1 << 13)), ((128, 32, 3, 16, 11, 1), 1 << 10),
+            ((64, 32, 1, 16, 7, 0), 1 << 10), ((16, 8, 3, 32, 301, 3), 1 << 10)]
 
 
 @pytest.mark.parametrize("cfg,mode", VARIANTS, ids=lambda v: str(v).replace(" ", ""))
