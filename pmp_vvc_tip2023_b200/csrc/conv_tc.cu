@@ -55,6 +55,9 @@ static int g_tc_scheme = -1;     // -1 auto, 0 unstacked, 1 stacked
 static int g_tc_pair = -1;       // -1 library default / env PMP_TC_PAIR, 0 single-CTA kernel, 1 CTA-pair kernel where applicable
 constexpr int TC_DEFAULT_PAIR = 1;
 
+// accumulator scheme of the CTA-pair kernel (baked into its weight image): stacked iff Cout <= 32
+static inline bool tc_pair_stacked_layout(int cout_pad) { return cout_pad <= 32; }
+
 static bool tc_pair_default()
 {
     static const int env_pair = [] { const char *e = getenv("PMP_TC_PAIR"); return e ? atoi(e) : TC_DEFAULT_PAIR; }();
@@ -98,9 +101,9 @@ static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W,
         return e ? atoi(e) : -1;
     }();
     const int scheme = scheme_override >= 0 ? scheme_override : (g_tc_scheme < 0 ? env_scheme : g_tc_scheme);
-    // auto: when the CTA-pair kernel is the default every layer runs the unstacked arithmetic (the pair kernel's), also
-    // in the single-CTA fallback (batch of 1), so results do not depend on batch composition bit for bit
-    g.stacked = scheme == 1 || (scheme < 0 && cout_pad <= 32 && !tc_pair_default());
+    // auto: stacked for Cout <= 32 (those layers are bound by the A-operand reads: 2 instead of 3 per tap), unstacked for
+    // Cout = 64.  Both kernels follow the same rule, so results do not depend on batch composition bit for bit.
+    g.stacked = scheme == 1 || (scheme < 0 && tc_pair_stacked_layout(cout_pad));
     g.pairbuf = g.stacked && 16 * cout_pad > 512;
     const int mt_max = g.pairbuf ? 2 : 4;
     for (int mt = (g.total_mt < mt_max ? g.total_mt : mt_max); mt >= 1; mt--) {
@@ -163,25 +166,51 @@ void pack_tc_weights(const float *w, int cout, int cin, int kh, int kw, int cin_
                     }
 }
 
-// CTA-pair operand image: [rank (2)][group][tap][k8 (2)][Cout_pad rows: w_hi[h*r..h*r+h) then w_lo[h*r..h*r+h), h = Cout_pad/2][8]
-size_t tc_pair_packed_elems(int cin_pad, int cout_pad, int kh, int kw) { return (size_t)2 * (cin_pad / 16) * kh * kw * 2 * cout_pad * 8; }
+// CTA-pair operand image: [rank (2)][group][tap] slabs, one per CTA and (group, tap):
+//   Cout = 64 (unstacked) : [k8 (2)][w_hi[h*r .. h*r+h) | w_lo[h*r .. h*r+h)][8], h = Cout/2            (32*Cout bytes)
+//   Cout <= 32 (stacked)  : [k8 (2)][this CTA's half of the N = 2*Cout operand [w_hi | w_lo] (rank 0: w_hi, rank 1:
+//                           w_lo; Cout rows) | this CTA's half of the N = Cout operand w_hi[h*r .. h*r+h)][8] (48*Cout bytes)
+static inline int tc_pair_slab_rows(int cout_pad) { return tc_pair_stacked_layout(cout_pad) ? cout_pad + cout_pad / 2 : cout_pad; }
+
+size_t tc_pair_packed_elems(int cin_pad, int cout_pad, int kh, int kw)
+{
+    return (size_t)2 * (cin_pad / 16) * kh * kw * 2 * tc_pair_slab_rows(cout_pad) * 8;
+}
 
 void pack_tc_pair_weights(const float *w, int cout, int cin, int kh, int kw, int cin_pad, int cout_pad, bool bf16, uint16_t *dst)
 {
-    const int groups = cin_pad / 16, taps = kh * kw, half = cout_pad / 2;
+    const int groups = cin_pad / 16, taps = kh * kw, half = cout_pad / 2, rows = tc_pair_slab_rows(cout_pad);
+    const bool st = tc_pair_stacked_layout(cout_pad);
+    auto weight = [&](int co, int c, int t, uint16_t &hi, uint16_t &lo) {
+        hi = lo = 0;
+        if (co < cout && c < cin) host_split(w[((size_t)co * cin + c) * taps + t], bf16, hi, lo);
+    };
     for (int r = 0; r < 2; r++)
         for (int g = 0; g < groups; g++)
             for (int t = 0; t < taps; t++)
-                for (int k8 = 0; k8 < 2; k8++)
-                    for (int n = 0; n < half; n++)
-                        for (int e = 0; e < 8; e++) {
-                            const int c = g * 16 + k8 * 8 + e, co = half * r + n;
-                            uint16_t hi = 0, lo = 0;
-                            if (co < cout && c < cin) host_split(w[((size_t)co * cin + c) * taps + t], bf16, hi, lo);
-                            const size_t base = ((((size_t)r * groups + g) * taps + t) * 2 + k8) * cout_pad * 8;
-                            dst[base + (size_t)n * 8 + e] = hi;
-                            dst[base + (size_t)(half + n) * 8 + e] = lo;
+                for (int k8 = 0; k8 < 2; k8++) {
+                    uint16_t *slab = dst + ((((size_t)r * groups + g) * taps + t) * 2 + k8) * rows * 8;
+                    for (int e = 0; e < 8; e++) {
+                        const int c = g * 16 + k8 * 8 + e;
+                        uint16_t hi, lo;
+                        if (st) {
+                            for (int n = 0; n < cout_pad; n++) {
+                                weight(n, c, t, hi, lo);
+                                slab[(size_t)n * 8 + e] = r == 0 ? hi : lo;
+                            }
+                            for (int n = 0; n < half; n++) {
+                                weight(half * r + n, c, t, hi, lo);
+                                slab[(size_t)(cout_pad + n) * 8 + e] = hi;
+                            }
+                        } else {
+                            for (int n = 0; n < half; n++) {
+                                weight(half * r + n, c, t, hi, lo);
+                                slab[(size_t)n * 8 + e] = hi;
+                                slab[(size_t)(half + n) * 8 + e] = lo;
+                            }
                         }
+                    }
+                }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -714,11 +743,11 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, u
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+struct PairGeom { int n, mt_count, q0, row0, qoff; bool store; };
+
 // per-CTA weight slab: [2 k8][Cout/2 w_hi rows | Cout/2 w_lo rows][8] 16-bit = 32 * Cout bytes (p.pair_slab).  A ring stage
 // holds one FILTER ROW of one channel group (kw consecutive slabs, contiguous in the packed image): one full/empty barrier
 // pair, one TMA request and one commit per row instead of per tap.
-
-struct PairGeom { int n, mt_count, q0, row0, qoff; bool store; };
 
 __device__ __forceinline__ PairGeom pair_geom(const TcParams &p, int item, int rank)
 {
@@ -742,7 +771,7 @@ struct PairBars { uint32_t afull, aempty, wfull, wempty, acc, accempty; };
 // instructions per filter row at IPC 0.1 -- so the loop is kept to the bare minimum: one barrier probe and one commit
 // per filter row (row-granular ring stages), the row's kw taps unrolled at compile time with descriptors that differ by
 // compile-time constants, every operand warp-uniform so that it lives in uniform registers.
-template <int KW>
+template <int KW, bool ST>
 __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b, uint32_t tmem_base, uint32_t act_addr,
                                             uint32_t ring_addr, int m, int cid, int ncl, bool prof, long long t_begin)
 {
@@ -752,8 +781,11 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
     const uint32_t act16 = (act_addr >> 4) + (uint32_t)m * 128u, ring16 = ring_addr >> 4;
     const uint32_t group16 = p.group_bytes >> 4, slab16 = p.pair_slab >> 4, row16 = (uint32_t)KW * slab16;
     const uint64_t lo16 = (2u * p.plane_bytes) >> 4;            // a_lo planes follow the two a_hi planes
-    const uint64_t wlo16 = (uint64_t)(p.coutp >> 1);            // this CTA's w_lo rows follow its w_hi rows
-    const uint32_t idesc = p.idesc1;
+    // unstacked: this CTA's w_lo rows follow its w_hi rows; stacked: its rows of the N = Cout operand follow its Cout
+    // rows of the N = 2*Cout operand
+    const uint64_t wlo16 = (uint64_t)(ST ? p.coutp : (p.coutp >> 1));
+    const uint32_t idesc = p.idesc1, idesc_st = p.idesc2;
+    const uint32_t acc_cols = ST ? 2u * (uint32_t)p.coutp : (uint32_t)p.coutp;
     const uint32_t peer_wempty = mapa_cluster(b.wempty, 1), peer_aempty = mapa_cluster(b.aempty, 1), peer_acc = mapa_cluster(b.acc, 1);
     const int KH = p.kh, P = p.P, NS = p.nstages, G = p.groups;
     long long st_a = 0, st_b = 0, st_c = 0;
@@ -763,7 +795,7 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
         const uint32_t buf = idx & 1u;
         const bool mine = m < t.mt_count;
         const uint32_t accidx = buf * 4u + (uint32_t)m;
-        const uint32_t d_tmem = tmem_base + accidx * (uint32_t)p.coutp;
+        const uint32_t d_tmem = tmem_base + accidx * acc_cols;
         {
             TC_PROF_BEGIN(prof);
             mbar_wait(b.accempty + 8 * accidx, ((idx >> 1) & 1u) ^ 1u);     // both CTAs drained it (tile idx-2)
@@ -785,9 +817,14 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
 #pragma unroll
                         for (int j = 0; j < KW; j++) {
                             const uint64_t ad = ad0 + (uint64_t)j, bd = bd0 + (uint64_t)((uint32_t)j * slab16);
-                            umma_f16_pair(d_tmem, ad, bd, idesc, j == 0 ? acc : 1u);    // a_hi * w_hi
-                            umma_f16_pair(d_tmem, ad, bd + wlo16, idesc, 1u);           // a_hi * w_lo
-                            umma_f16_pair(d_tmem, ad + lo16, bd, idesc, 1u);            // a_lo * w_hi
+                            if (ST) {
+                                umma_f16_pair(d_tmem, ad, bd, idesc_st, j == 0 ? acc : 1u);     // a_hi * [w_hi | w_lo]
+                                umma_f16_pair(d_tmem, ad + lo16, bd + wlo16, idesc, 1u);        // a_lo * w_hi
+                            } else {
+                                umma_f16_pair(d_tmem, ad, bd, idesc, j == 0 ? acc : 1u);        // a_hi * w_hi
+                                umma_f16_pair(d_tmem, ad, bd + wlo16, idesc, 1u);               // a_hi * w_lo
+                                umma_f16_pair(d_tmem, ad + lo16, bd, idesc, 1u);                // a_lo * w_hi
+                            }
                         }
                         umma_commit_pair(b.wempty + 8 * s);                             // row free when read
                     } else {
@@ -898,9 +935,16 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         if (rank == 0) {
             // ===== MMA issuers (leader only) =====
             const int m = warp - 2;
-            if (p.kw == 3) pair_issuer<3>(p, b, tmem_base, smem_u32(act), smem_u32(ring), m, cid, ncl, prof, t_begin);
-            else if (p.kw == 5) pair_issuer<5>(p, b, tmem_base, smem_u32(act), smem_u32(ring), m, cid, ncl, prof, t_begin);
-            else pair_issuer<1>(p, b, tmem_base, smem_u32(act), smem_u32(ring), m, cid, ncl, prof, t_begin);
+            const uint32_t aa = smem_u32(act), ra = smem_u32(ring);
+            if (p.stacked) {
+                if (p.kw == 3) pair_issuer<3, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
+                else if (p.kw == 5) pair_issuer<5, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
+                else pair_issuer<1, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
+            } else {
+                if (p.kw == 3) pair_issuer<3, false>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
+                else if (p.kw == 5) pair_issuer<5, false>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
+                else pair_issuer<1, false>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
+            }
         }
     } else {
         // ===== epilogue (both CTAs, own accumulators; the drain is reported to the leader) =====
@@ -934,7 +978,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
                     const int r = pos / p.P, c = pos - r * p.P;
                     const bool valid = t.store && (c < p.W) && (r < p.H);
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + accidx * (uint32_t)p.coutp;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + accidx * (uint32_t)(p.stacked ? p.N1 : p.coutp);
                     if (chh == 4) epilogue_chunks<4>(p, taddr, ch0, t.n, r, c, valid);
                     else
                         for (int j = 0; j < chh; j++) epilogue_chunks<1>(p, taddr, ch0 + j, t.n, r, c, valid);
@@ -1033,12 +1077,12 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         h->tc_attr_set = true;
     }
     const double flops = a.flops_override > 0 ? a.flops_override * B : 2.0 * B * H * W * (double)a.out.C * a.in.C * a.kh * a.kw;
-    if (tc_pair_default() && B >= 2 && a.w_pair && !g.stacked) {
+    if (tc_pair_default() && B >= 2 && a.w_pair && (g.stacked != 0) == tc_pair_stacked_layout(g.coutp) && !g.pairbuf) {
         // CTA-pair kernel: 2-D tensor map over this conv's per-CTA weight slabs (8-byte elements, one slab per map row);
         // one box = one filter row of one channel group = kw consecutive slabs = one ring stage
         CUtensorMap tmap_w;
         const cuuint64_t nslab = (cuuint64_t)2 * g.groups * a.kh * a.kw;
-        const uint32_t slab = 32u * (uint32_t)g.coutp;                   // <= 2 KB = 256 elements
+        const uint32_t slab = 32u * (uint32_t)tc_pair_slab_rows(g.coutp);        // <= 2 KB = 256 elements
         cuuint64_t wdim[2] = {slab / 8, nslab};
         cuuint64_t wstr[1] = {slab};
         cuuint32_t wbox[2] = {slab / 8, (cuuint32_t)a.kw};
@@ -1052,14 +1096,15 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         }
         p.B = B;
         p.pair_items = g.tiles * ((B + 1) / 2);
-        p.stacked = 0; p.pairbuf = 0; p.pair_slab = slab;
+        p.pairbuf = 0; p.pair_slab = slab;
         uint32_t pc = 32;
-        while (pc < 8u * (uint32_t)g.coutp) pc <<= 1;           // 4 M-tiles x 2 buffers x Cout columns
+        while (pc < (g.stacked ? 16u : 8u) * (uint32_t)g.coutp) pc <<= 1;        // 4 M-tiles x 2 buffers x (2*)Cout columns
         p.tmem_cols = pc;
         tc_ring_layout(g, slab * (uint32_t)a.kw, a.kh);           // ring stages are filter rows
         p.nstages = g.nstages; p.nbuf = g.nbuf;
         const uint32_t smem_pair = g.smem_bytes;
         p.idesc1 = idesc_base_nom | ((uint32_t)(g.coutp >> 3) << 17) | ((256u >> 4) << 24);      // M = 256 across the pair
+        p.idesc2 = idesc_base_nom | ((uint32_t)(g.N1 >> 3) << 17) | ((256u >> 4) << 24);         // stacked: N = 2*Cout
         int nsm = h->num_sms & ~1;
         int grid = 2 * p.pair_items < nsm ? 2 * p.pair_items : nsm;
         ProfScope ps(h, PROF_CONV_TC, s, flops, 0);
