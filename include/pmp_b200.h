@@ -134,7 +134,8 @@ int pmp_run_component(pmp_handle *h, int wset_q, int wset_msbd, int luma, const 
 /* Self-test of the TC conv engine against the SIMT engine on random data (GPU).  Returns 0 and the
  * max-abs error in *max_err, or an error.  flags: bit0 ReLU, bit1 identity residual, bit2 attention product,
  * bit3 bf16 operands; kernel variants: bits 8..9 accumulator scheme of the single-CTA kernel (1 unstacked, 2 stacked),
- * bit10 CTA-pair (cta_group::2) kernel, bit11 force the single-CTA kernel, bits 13..15 cap on the number of whole-tile
+ * bit10 CTA-pair (cta_group::2) kernel, bit11 force the single-CTA kernel, bit12 unstacked accumulators for the
+ * 3x3 Cout = 64 layers (A/B of the default stacked scheme), bits 13..15 cap on the number of whole-tile
  * activation buffers (0: default); bit16 verbose mismatch report on stderr. */
 int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, int hw, int batch, int flags,
                       double *max_err, double *ref_absmax, double *ms_tc, double *ms_simt);

@@ -55,8 +55,16 @@ static int g_tc_scheme = -1;     // -1 auto, 0 unstacked, 1 stacked
 static int g_tc_pair = -1;       // -1 library default / env PMP_TC_PAIR, 0 single-CTA kernel, 1 CTA-pair kernel where applicable
 constexpr int TC_DEFAULT_PAIR = 1;
 
-// accumulator scheme of the CTA-pair kernel (baked into its weight image): stacked iff Cout <= 32
-static inline bool tc_pair_stacked_layout(int cout_pad) { return cout_pad <= 32; }
+// Accumulator scheme (baked into the CTA-pair kernel's weight image): stacked for Cout <= 32 and for the 3x3 Cout = 64
+// layers (half of all conv time; they run at the shared-memory operand floor, which stacking lowers from 15 to 11 KB per
+// K step), unstacked for the rest (5x5: no shared memory left for row stages of 3 KB slabs; 1x1: bandwidth-bound).
+static int g_tc_st64 = -1;       // -1 library default / env PMP_TC_ST64
+static inline bool tc_pair_stacked_layout(int cout_pad, int kh, int kw)
+{
+    static const int env_st64 = [] { const char *e = getenv("PMP_TC_ST64"); return e ? atoi(e) : 1; }();
+    const bool st64 = (g_tc_st64 < 0 ? env_st64 : g_tc_st64) != 0;
+    return cout_pad <= 32 || (st64 && cout_pad == 64 && kh == 3 && kw == 3);
+}
 
 static bool tc_pair_default()
 {
@@ -84,7 +92,7 @@ static void tc_ring_layout(TcGeom &g, uint32_t slab, int taps)
     g.smem_bytes = TC_SMEM_HEADER + (uint32_t)nb * g.act_bytes + (uint32_t)g.nstages * slab;
 }
 
-static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W, TcGeom &g, int scheme_override = -1)
+static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W, TcGeom &g, int scheme_override = -1, bool pair = false)
 {
     if (kh < 1 || kh > 9 || kw < 1 || kw > 5) return false;
     if (cin_pad % 16 || cout_pad % 16 || cin_pad < 16 || cout_pad < 16 || cout_pad > 64) return false;
@@ -103,9 +111,11 @@ static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W,
     const int scheme = scheme_override >= 0 ? scheme_override : (g_tc_scheme < 0 ? env_scheme : g_tc_scheme);
     // auto: stacked for Cout <= 32 (those layers are bound by the A-operand reads: 2 instead of 3 per tap), unstacked for
     // Cout = 64.  Both kernels follow the same rule, so results do not depend on batch composition bit for bit.
-    g.stacked = scheme == 1 || (scheme < 0 && tc_pair_stacked_layout(cout_pad));
-    g.pairbuf = g.stacked && 16 * cout_pad > 512;
-    const int mt_max = g.pairbuf ? 2 : 4;
+    g.stacked = scheme == 1 || (scheme < 0 && tc_pair_stacked_layout(cout_pad, kh, kw));
+    // stacked Cout = 64 needs 128 columns per accumulator: the single-CTA kernel runs 2 M-tiles x 2 buffers ("pairbuf"),
+    // the pair kernel 3 M-tiles on a ring of 4 accumulator slots
+    g.pairbuf = !pair && g.stacked && 16 * cout_pad > 512;
+    const int mt_max = g.pairbuf ? 2 : (pair && g.stacked && 16 * cout_pad > 512 ? 3 : 4);
     for (int mt = (g.total_mt < mt_max ? g.total_mt : mt_max); mt >= 1; mt--) {
         int maxidx = g.P - 1 + mt * 128 - 1 + (kh - 1) * g.P + (kw - 1);
         int rbox = maxidx / g.P + 1;
@@ -117,6 +127,7 @@ static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W,
         tc_ring_layout(g, g.stage_bytes, kh * kw);
         g.tiles = (g.total_mt + mt - 1) / mt;
         uint32_t cols = (g.stacked && !g.pairbuf ? 16u : 8u) * g.coutp, pc = 32;
+        if (cols > 512) cols = 512;                  // pair kernel, stacked Cout = 64: 4 slots of 128 columns
         while (pc < cols) pc <<= 1;
         g.tmem_cols = pc;
         return pc <= 512;
@@ -167,20 +178,23 @@ void pack_tc_weights(const float *w, int cout, int cin, int kh, int kw, int cin_
 }
 
 // CTA-pair operand image: [rank (2)][group][tap] slabs, one per CTA and (group, tap):
-//   Cout = 64 (unstacked) : [k8 (2)][w_hi[h*r .. h*r+h) | w_lo[h*r .. h*r+h)][8], h = Cout/2            (32*Cout bytes)
-//   Cout <= 32 (stacked)  : [k8 (2)][this CTA's half of the N = 2*Cout operand [w_hi | w_lo] (rank 0: w_hi, rank 1:
+//   unstacked : [k8 (2)][w_hi[h*r .. h*r+h) | w_lo[h*r .. h*r+h)][8], h = Cout/2                        (32*Cout bytes)
+//   stacked   : [k8 (2)][this CTA's half of the N = 2*Cout operand [w_hi | w_lo] (rank 0: w_hi, rank 1:
 //                           w_lo; Cout rows) | this CTA's half of the N = Cout operand w_hi[h*r .. h*r+h)][8] (48*Cout bytes)
-static inline int tc_pair_slab_rows(int cout_pad) { return tc_pair_stacked_layout(cout_pad) ? cout_pad + cout_pad / 2 : cout_pad; }
+static inline int tc_pair_slab_rows(int cout_pad, int kh, int kw)
+{
+    return tc_pair_stacked_layout(cout_pad, kh, kw) ? cout_pad + cout_pad / 2 : cout_pad;
+}
 
 size_t tc_pair_packed_elems(int cin_pad, int cout_pad, int kh, int kw)
 {
-    return (size_t)2 * (cin_pad / 16) * kh * kw * 2 * tc_pair_slab_rows(cout_pad) * 8;
+    return (size_t)2 * (cin_pad / 16) * kh * kw * 2 * tc_pair_slab_rows(cout_pad, kh, kw) * 8;
 }
 
 void pack_tc_pair_weights(const float *w, int cout, int cin, int kh, int kw, int cin_pad, int cout_pad, bool bf16, uint16_t *dst)
 {
-    const int groups = cin_pad / 16, taps = kh * kw, half = cout_pad / 2, rows = tc_pair_slab_rows(cout_pad);
-    const bool st = tc_pair_stacked_layout(cout_pad);
+    const int groups = cin_pad / 16, taps = kh * kw, half = cout_pad / 2, rows = tc_pair_slab_rows(cout_pad, kh, kw);
+    const bool st = tc_pair_stacked_layout(cout_pad, kh, kw);
     auto weight = [&](int co, int c, int t, uint16_t &hi, uint16_t &lo) {
         hi = lo = 0;
         if (co < cout && c < cin) host_split(w[((size_t)co * cin + c) * taps + t], bf16, hi, lo);
@@ -319,8 +333,10 @@ struct TcParams {
     int H, W, P, kh, kw, pady, padx, groups, total_mt, tiles, N1, coutp, nstages, items;
     uint32_t plane_bytes, group_bytes, stage_bytes, tmem_cols, idesc1, idesc2;
     int relu, stacked, pairbuf, nbuf, dbg, prefetch;
+    int nslot, mt_alloc, acc_cols;      // CTA-pair kernel: accumulator slot ring (slots, M-tiles per tile, columns per slot)
     int B, pair_items;      // CTA-pair kernel: images in the batch, work items = tiles * ceil(B/2)
     uint32_t pair_slab;     // CTA-pair kernel: bytes of one per-CTA weight slab
+    int pair_split;         // CTA-pair kernel: rows of the weight tensor map per slab (1, or 2 for 3 KB slabs)
 };
 
 struct TileGeom { int n, mt_count, q0, row0, qoff; };
@@ -785,23 +801,23 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
     // rows of the N = 2*Cout operand
     const uint64_t wlo16 = (uint64_t)(ST ? p.coutp : (p.coutp >> 1));
     const uint32_t idesc = p.idesc1, idesc_st = p.idesc2;
-    const uint32_t acc_cols = ST ? 2u * (uint32_t)p.coutp : (uint32_t)p.coutp;
+    const uint32_t acc_cols = (uint32_t)p.acc_cols, NSLOT = (uint32_t)p.nslot, MTA = (uint32_t)p.mt_alloc;
+    const bool has_slot = (uint32_t)m < MTA;
+    uint32_t slot = (uint32_t)m, sph = 0;       // this issuer's accumulator slot for the current tile, parity of its use count
     const uint32_t peer_wempty = mapa_cluster(b.wempty, 1), peer_aempty = mapa_cluster(b.aempty, 1), peer_acc = mapa_cluster(b.acc, 1);
     const int KH = p.kh, P = p.P, NS = p.nstages, G = p.groups;
     long long st_a = 0, st_b = 0, st_c = 0;
     uint32_t s = 0, ph = 0, idx = 0, ab = 0, aph = 0;
     for (int item = cid; item < p.pair_items; item += ncl, idx++) {
         const PairGeom t = pair_geom(p, item, 0);
-        const uint32_t buf = idx & 1u;
         const bool mine = m < t.mt_count;
-        const uint32_t accidx = buf * 4u + (uint32_t)m;
-        const uint32_t d_tmem = tmem_base + accidx * acc_cols;
-        {
+        const uint32_t d_tmem = tmem_base + slot * acc_cols;
+        if (has_slot) {
             TC_PROF_BEGIN(prof);
-            mbar_wait(b.accempty + 8 * accidx, ((idx >> 1) & 1u) ^ 1u);     // both CTAs drained it (tile idx-2)
+            mbar_wait(b.accempty + 8 * slot, sph ^ 1u);          // both CTAs drained its previous use
             TC_PROF_END(prof, st_a);
+            tc_fence_after();
         }
-        tc_fence_after();
         uint32_t acc = 0;
         for (int g = 0; g < G; g++) {
             const uint32_t slot = ab * (uint32_t)G + (uint32_t)g;
@@ -842,11 +858,15 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
             }
             __syncwarp();
         }
-        if (elect_one_sync()) {                                  // accumulators of this tile complete
-            if (mine) umma_commit_pair(b.acc + 8 * buf);
-            else { mbar_arrive(b.acc + 8 * buf); mbar_arrive_cluster_relaxed(peer_acc + 8 * buf); }
+        if (has_slot) {
+            if (elect_one_sync()) {                              // this M-tile's accumulator is complete
+                if (mine) umma_commit_pair(b.acc + 8 * slot);
+                else { mbar_arrive(b.acc + 8 * slot); mbar_arrive_cluster_relaxed(peer_acc + 8 * slot); }
+            }
+            __syncwarp();
+            slot += MTA;
+            if (slot >= NSLOT) { slot -= NSLOT; sph ^= 1u; }
         }
-        __syncwarp();
         if (++ab == (uint32_t)p.nbuf) { ab = 0; aph ^= 1u; }
     }
     if (prof && m == 0 && (threadIdx.x & 31) == 0) {
@@ -863,7 +883,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     // same barrier slots as conv_tc_kernel; a weight stage is a filter row here
     PairBars b;
     b.afull = smem_u32(bars); b.aempty = smem_u32(bars + 16); b.wfull = smem_u32(bars + 32);
-    b.wempty = smem_u32(bars + 56); b.acc = smem_u32(bars + 80); b.accempty = smem_u32(bars + 82);
+    b.wempty = smem_u32(bars + 56); b.acc = smem_u32(bars + 80); b.accempty = smem_u32(bars + 88);     // 8 + 8 accumulator slots
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 1008);
     uint8_t *act = smem + TC_SMEM_HEADER;
     uint8_t *ring = act + (size_t)p.nbuf * p.groups * p.group_bytes;
@@ -878,9 +898,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     if (threadIdx.x == 0) {
         for (int g = 0; g < p.nbuf * p.groups; g++) { mbar_init(b.afull + 8 * g, 1); mbar_init(b.aempty + 8 * g, TC_MMA_WARPS); }
         for (int s = 0; s < p.nstages; s++) { mbar_init(b.wfull + 8 * s, 1); mbar_init(b.wempty + 8 * s, TC_MMA_WARPS); }
-        mbar_init(b.acc, TC_MMA_WARPS);
-        mbar_init(b.acc + 8, TC_MMA_WARPS);
-        for (int m = 0; m < 8; m++) mbar_init(b.accempty + 8 * m, 2 * TC_EPI_WARPS);
+        for (int m = 0; m < p.nslot; m++) { mbar_init(b.acc + 8 * m, 1); mbar_init(b.accempty + 8 * m, 2 * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -906,7 +924,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 for (int it = 0; it < rows_per_item; it++) {
                     { TC_PROF_BEGIN(prof); mbar_wait_relaxed(b.wempty + 8 * s, ph ^ 1u); TC_PROF_END(prof, st); }
                     if (rank == 0) mbar_expect_tx(b.wfull + 8 * s, 2u * row_bytes);
-                    tma_load_2d_pair(smem_u32(ring) + s * row_bytes, &tmap_w, lead_wfull + 8 * s, 0, slab0 + it * p.kw);
+                    tma_load_2d_pair(smem_u32(ring) + s * row_bytes, &tmap_w, lead_wfull + 8 * s, 0, (slab0 + it * p.kw) * p.pair_split);
                     if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -952,8 +970,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         const int nchunk = p.coutp >> 3, chh = nchunk >> 1, ch0 = half * chh;
         const uint32_t lead_accempty = mapa_cluster(b.accempty, 0);
         long long st = 0;
-        uint32_t idx = 0;
-        for (int item = cid; item < p.pair_items; item += ncl, idx++) {
+        uint32_t slot0 = 0, ph0 = 0;            // accumulator slot of this tile's M-tile 0, parity of its use count
+        for (int item = cid; item < p.pair_items; item += ncl) {
             const PairGeom t = pair_geom(p, item, (int)rank);
             if ((p.res.p || p.mul.p) && (lane & 7) == 0) {
                 const size_t plane = (size_t)p.H * p.W;
@@ -969,16 +987,16 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     }
                 }
             }
-            const uint32_t buf = idx & 1u;
-            { TC_PROF_BEGIN(prof); mbar_wait_relaxed(b.acc + 8 * buf, (idx >> 1) & 1u); TC_PROF_END(prof, st); }
-            tc_fence_after();
-            for (int mt = 0; mt < 4; mt++) {
-                const uint32_t accidx = 4u * buf + (uint32_t)mt;
+            for (int mt = 0; mt < p.mt_alloc; mt++) {
+                uint32_t sl = slot0 + (uint32_t)mt, par = ph0;
+                if (sl >= (uint32_t)p.nslot) { sl -= (uint32_t)p.nslot; par ^= 1u; }
+                { TC_PROF_BEGIN(prof); mbar_wait_relaxed(b.acc + 8 * sl, par); TC_PROF_END(prof, st); }
                 if (mt < t.mt_count) {
+                    tc_fence_after();
                     const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
                     const int r = pos / p.P, c = pos - r * p.P;
                     const bool valid = t.store && (c < p.W) && (r < p.H);
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + accidx * (uint32_t)(p.stacked ? p.N1 : p.coutp);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + sl * (uint32_t)p.acc_cols;
                     if (chh == 4) epilogue_chunks<4>(p, taddr, ch0, t.n, r, c, valid);
                     else
                         for (int j = 0; j < chh; j++) epilogue_chunks<1>(p, taddr, ch0 + j, t.n, r, c, valid);
@@ -986,10 +1004,12 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 }
                 __syncwarp();
                 if (lane == 0) {        // TMEM reads are complete (wait::ld); nothing else needs ordering with this arrival
-                    if (rank == 0) mbar_arrive(b.accempty + 8 * accidx);
-                    else mbar_arrive_cluster_relaxed(lead_accempty + 8 * accidx);
+                    if (rank == 0) mbar_arrive(b.accempty + 8 * sl);
+                    else mbar_arrive_cluster_relaxed(lead_accempty + 8 * sl);
                 }
             }
+            slot0 += (uint32_t)p.mt_alloc;
+            if (slot0 >= (uint32_t)p.nslot) { slot0 -= (uint32_t)p.nslot; ph0 ^= 1u; }
         }
         if (prof && lane == 0 && warp == 2 + TC_MMA_WARPS) {
             unsigned long long *o = g_tc_stalls + blockIdx.x * TC_PROF_SLOTS;
@@ -1031,7 +1051,12 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     if (B <= 0) return PMP_OK;
     TcGeom g;
     const int H = a.Ho ? a.Ho : a.in.H, W = a.in.W, Hin = a.in.H;
-    if (a.in.fmt != FMT_SPLIT || a.out.fmt != FMT_SPLIT || !tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g) ||
+    const bool want_pair = tc_pair_default() && B >= 2 && a.w_pair;
+    bool geom_ok = want_pair && tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g, -1, true) &&
+                   (g.stacked != 0) == tc_pair_stacked_layout(a.cout_pad, a.kh, a.kw);
+    const bool use_pair = geom_ok;
+    if (!geom_ok) geom_ok = tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g);
+    if (a.in.fmt != FMT_SPLIT || a.out.fmt != FMT_SPLIT || !geom_ok ||
         a.in.Cp != a.cin_pad || a.out.Cp != a.cout_pad || a.pool != 1 || a.out.H != H || a.out.W != W) {
         set_error("conv_tc: unsupported configuration cin %d cout %d k %dx%d %dx%d", a.cin_pad, a.cout_pad, a.kh, a.kw, H, W);
         return PMP_ERR_UNSUPPORTED;
@@ -1077,15 +1102,17 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         h->tc_attr_set = true;
     }
     const double flops = a.flops_override > 0 ? a.flops_override * B : 2.0 * B * H * W * (double)a.out.C * a.in.C * a.kh * a.kw;
-    if (tc_pair_default() && B >= 2 && a.w_pair && (g.stacked != 0) == tc_pair_stacked_layout(g.coutp) && !g.pairbuf) {
+    if (use_pair) {
         // CTA-pair kernel: 2-D tensor map over this conv's per-CTA weight slabs (8-byte elements, one slab per map row);
         // one box = one filter row of one channel group = kw consecutive slabs = one ring stage
         CUtensorMap tmap_w;
         const cuuint64_t nslab = (cuuint64_t)2 * g.groups * a.kh * a.kw;
-        const uint32_t slab = 32u * (uint32_t)tc_pair_slab_rows(g.coutp);        // <= 2 KB = 256 elements
-        cuuint64_t wdim[2] = {slab / 8, nslab};
-        cuuint64_t wstr[1] = {slab};
-        cuuint32_t wbox[2] = {slab / 8, (cuuint32_t)a.kw};
+        // (slabs above 2 KB = 256 elements -- stacked Cout = 64: 3 KB -- take two map rows, one per k8 half)
+        const uint32_t slab = 32u * (uint32_t)tc_pair_slab_rows(g.coutp, a.kh, a.kw);
+        const uint32_t split = slab > 2048u ? 2u : 1u;
+        cuuint64_t wdim[2] = {slab / split / 8, nslab * split};
+        cuuint64_t wstr[1] = {slab / split};
+        cuuint32_t wbox[2] = {slab / split / 8, (cuuint32_t)a.kw * split};
         cuuint32_t west[2] = {1, 1};
         cr = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void *)a.w_pair, wdim, wstr, wbox, west,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1096,10 +1123,14 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         }
         p.B = B;
         p.pair_items = g.tiles * ((B + 1) / 2);
-        p.pairbuf = 0; p.pair_slab = slab;
-        uint32_t pc = 32;
-        while (pc < (g.stacked ? 16u : 8u) * (uint32_t)g.coutp) pc <<= 1;        // 4 M-tiles x 2 buffers x (2*)Cout columns
-        p.tmem_cols = pc;
+        p.pairbuf = 0; p.pair_slab = slab; p.pair_split = (int)split;
+        // accumulator slot ring: 8 slots of (2*)Cout columns, tiles of up to 4 M-tiles (= two alternating buffers); stacked
+        // Cout = 64: 4 slots of 128 columns, tiles of up to 3 M-tiles -- the 4th slot lets the next tile start while the
+        // epilogue drains this one slot by slot
+        p.acc_cols = (g.stacked ? 2 : 1) * g.coutp;
+        p.nslot = 512 / p.acc_cols < 8 ? 512 / p.acc_cols : 8;
+        p.mt_alloc = p.nslot < 8 ? 3 : 4;
+        p.tmem_cols = g.tmem_cols;
         tc_ring_layout(g, slab * (uint32_t)a.kw, a.kh);           // ring stages are filter rows
         p.nstages = g.nstages; p.nbuf = g.nbuf;
         const uint32_t smem_pair = g.smem_bytes;
@@ -1265,6 +1296,10 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     PMP_CUDA(cudaSetDevice(h->device));
     const int B = batch, H = hw, W = hw;
     const bool bf = (flags & 8) != 0;
+    struct KnobReset {      // the variant knobs are process-wide: restore the defaults on every exit path
+        ~KnobReset() { pmp::g_tc_scheme = -1; pmp::g_tc_pair = -1; pmp::g_tc_nbuf_max = -1; pmp::g_tc_st64 = -1; }
+    } knob_reset;
+    pmp::g_tc_st64 = (flags >> 12) & 1 ? 0 : -1;         // bit 12: unstacked accumulators for the 3x3 Cout = 64 layers (A/B)
     const int cinp = pad16(cin), coutp = pad16(cout);
     if (!tc_supported(cinp, coutp, ksize, ksize, H, W)) {
         set_error("selftest: configuration not supported by the TC engine");
@@ -1355,12 +1390,11 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     pmp::g_tc_scheme = ((flags >> 8) & 3) - 1;          // 0: library default, 1: unstacked, 2: stacked
     pmp::g_tc_pair = (flags >> 10) & 1 ? 1 : ((flags >> 11) & 1 ? 0 : -1);   // bit 10: CTA-pair kernel, bit 11: force single
     pmp::g_tc_nbuf_max = ((flags >> 13) & 7) ? ((flags >> 13) & 7) : -1;      // bits 13..15: cap on activation buffers (0: default)
-    if (!tc_supported(cinp, coutp, ksize, ksize, H, W)) { pmp::g_tc_scheme = -1; set_error("selftest: scheme not supported"); return PMP_ERR_UNSUPPORTED; }
+    if (!tc_supported(cinp, coutp, ksize, ksize, H, W)) { set_error("selftest: scheme not supported"); return PMP_ERR_UNSUPPORTED; }
     rc = conv_tc(h, ta, B, s);          // warm-up (also first-launch overheads)
     cudaEventRecord(e2, s);
     if (!rc) rc = conv_tc(h, ta, B, s);
     cudaEventRecord(e3, s);
-    pmp::g_tc_scheme = -1; pmp::g_tc_pair = -1; pmp::g_tc_nbuf_max = -1;
     if (rc) return rc;
     split_to_f32_kernel<<<1024, 256, 0, s>>>(out, (float *)d_out32.p, B);
     cudaError_t ce = cudaStreamSynchronize(s);

@@ -29,7 +29,11 @@ VARIANTS = [((64, 64, 3, 32, 5, 3), 1 << 11), ((64, 64, 3, 32, 5, 3), 1 << 10), 
             ((64, 32, 3, 16, 7, 1), 1 << 10), ((64, 32, 3, 16, 7, 1), (1 << 11) | (2 << 8)), ((3, 32, 3, 16, 4, 1), 1 << 10),
             ((32, 64, 3, 32, 3, 7), 1 << 10), ((32, 64, 5, 64, 2, 1), 1 << 10), ((64, 64, 5, 64, 5, 3), 1 << 10),
             ((32, 16, 3, 16, 9, 3), 1 << 10), ((32, 16, 3, 16, 9, 3), (1 << 10) | (1 << 13)), ((128, 32, 3, 16, 11, 1), 1 << 10),
-            ((64, 32, 1, 16, 7, 0), 1 << 10), ((16, 8, 3, 32, 301, 3), 1 << 10)]
+            ((64, 32, 1, 16, 7, 0), 1 << 10), ((16, 8, 3, 32, 301, 3), 1 << 10),
+            # 3x3 Cout = 64: default stacked scheme on the 4-slot accumulator ring vs the unstacked A/B variant (bit 12),
+            # enough tiles per cluster to wrap the slot ring and the weight ring many times
+            ((64, 64, 3, 64, 150, 3), 1 << 10), ((64, 64, 3, 64, 150, 3), (1 << 10) | (1 << 12)), ((64, 64, 3, 32, 333, 7), 1 << 10),
+            ((64, 64, 3, 16, 75, 7), 1 << 10), ((32, 64, 3, 32, 5, 1), 1 << 11)]
 
 
 @pytest.mark.parametrize("cfg,mode", VARIANTS, ids=lambda v: str(v).replace(" ", ""))
