@@ -55,15 +55,18 @@ static int g_tc_scheme = -1;     // -1 auto, 0 unstacked, 1 stacked
 static int g_tc_pair = -1;       // -1 library default / env PMP_TC_PAIR, 0 single-CTA kernel, 1 CTA-pair kernel where applicable
 constexpr int TC_DEFAULT_PAIR = 1;
 
-// Accumulator scheme (baked into the CTA-pair kernel's weight image): stacked for Cout <= 32 and for the 3x3 Cout = 64
-// layers (half of all conv time; they run at the shared-memory operand floor, which stacking lowers from 15 to 11 KB per
-// K step), unstacked for the rest (5x5: no shared memory left for row stages of 3 KB slabs; 1x1: bandwidth-bound).
+// Accumulator scheme (baked into the CTA-pair kernel's weight image): stacked (2 MMAs per tap, 11 instead of 15 KB of
+// shared-memory operand reads per K step) for everything except the 1x1 Cout = 64 shortcuts (bandwidth-bound).  The
+// Cout = 64 layers then need 128 accumulator columns per M-tile: PMP_TC_ST64 = 0 keeps them all unstacked, 1 stacks the
+// 3x3 ones only, 2 (default) the 3x3 and 5x5 ones (A/B knob).
 static int g_tc_st64 = -1;       // -1 library default / env PMP_TC_ST64
 static inline bool tc_pair_stacked_layout(int cout_pad, int kh, int kw)
 {
-    static const int env_st64 = [] { const char *e = getenv("PMP_TC_ST64"); return e ? atoi(e) : 1; }();
-    const bool st64 = (g_tc_st64 < 0 ? env_st64 : g_tc_st64) != 0;
-    return cout_pad <= 32 || (st64 && cout_pad == 64 && kh == 3 && kw == 3);
+    static const int env_st64 = [] { const char *e = getenv("PMP_TC_ST64"); return e ? atoi(e) : 2; }();
+    const int st64 = g_tc_st64 < 0 ? env_st64 : g_tc_st64;
+    if (cout_pad <= 32) return true;
+    if (cout_pad != 64 || kh != kw) return false;
+    return (st64 >= 1 && kh == 3) || (st64 >= 2 && kh == 5);
 }
 
 static bool tc_pair_default()
@@ -337,6 +340,7 @@ struct TcParams {
     int B, pair_items;      // CTA-pair kernel: images in the batch, work items = tiles * ceil(B/2)
     uint32_t pair_slab;     // CTA-pair kernel: bytes of one per-CTA weight slab
     int pair_split;         // CTA-pair kernel: rows of the weight tensor map per slab (1, or 2 for 3 KB slabs)
+    int kws;                // CTA-pair kernel: taps per ring stage (kw = one filter row, or 1 when rows do not fit)
 };
 
 struct TileGeom { int n, mt_count, q0, row0, qoff; };
@@ -796,6 +800,7 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
     const uint64_t bdesc_c = desc_c | ((uint64_t)(p.pair_slab >> 5) << 16);                      // LBO = slab rows per k8
     const uint32_t act16 = (act_addr >> 4) + (uint32_t)m * 128u, ring16 = ring_addr >> 4;
     const uint32_t group16 = p.group_bytes >> 4, slab16 = p.pair_slab >> 4, row16 = (uint32_t)KW * slab16;
+    const int RS = p.kw / KW;                    // ring stages per filter row (1, or kw single-tap stages)
     const uint64_t lo16 = (2u * p.plane_bytes) >> 4;            // a_lo planes follow the two a_hi planes
     // unstacked: this CTA's w_lo rows follow its w_hi rows; stacked: its rows of the N = Cout operand follow its Cout
     // rows of the N = 2*Cout operand
@@ -823,10 +828,10 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
             const uint32_t slot = ab * (uint32_t)G + (uint32_t)g;
             { TC_PROF_BEGIN(prof); mbar_wait(b.afull + 8 * slot, aph); TC_PROF_END(prof, st_b); }
             uint32_t arow = act16 + slot * group16 + (uint32_t)t.qoff;
-            for (int ky = 0; ky < KH; ky++, arow += (uint32_t)P) {
+            for (int kr = 0, sx = 0; kr < KH * RS; kr++) {
                 { TC_PROF_BEGIN(prof); mbar_wait(b.wfull + 8 * s, ph); TC_PROF_END(prof, st_c); }
                 tc_fence_after();
-                const uint64_t ad0 = adesc_c | (uint64_t)arow;
+                const uint64_t ad0 = adesc_c | (uint64_t)(arow + (uint32_t)(sx * KW));
                 const uint64_t bd0 = bdesc_c | (uint64_t)(ring16 + s * row16);
                 if (elect_one_sync()) {
                     if (mine) {
@@ -851,6 +856,7 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
                 __syncwarp();
                 acc = 1u;
                 if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
+                if (++sx == RS) { sx = 0; arow += (uint32_t)P; }
             }
             if (elect_one_sync()) {                              // activation buffer free for a later tile
                 if (mine) umma_commit_pair(b.aempty + 8 * slot);
@@ -910,21 +916,26 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, cluster rendezvous) may overlap the
+    // tail of the previous kernel in the stream; nothing below touches global memory before that kernel has completed.
+    // The next kernel's CTAs may in turn be scheduled onto SMs as this grid's CTAs retire.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         if (lane == 0) {
             // ===== weight producer: this CTA's half of every (group, filter row) stage; bytes are counted on the leader =====
-            const int rows_per_item = p.kh * p.groups;
-            const uint32_t row_bytes = (uint32_t)p.kw * p.pair_slab;
+            const int rows_per_item = p.kh * (p.kw / p.kws) * p.groups;          // ring stages per tile
+            const uint32_t row_bytes = (uint32_t)p.kws * p.pair_slab;
             const uint32_t lead_wfull = mapa_cluster(b.wfull, 0);
-            const int slab0 = (int)rank * rows_per_item * p.kw;
+            const int slab0 = (int)rank * rows_per_item * p.kws;                   // this CTA's half of the image
             long long st = 0;
             uint32_t s = 0, ph = 0;
             for (int item = cid; item < p.pair_items; item += ncl) {
                 for (int it = 0; it < rows_per_item; it++) {
                     { TC_PROF_BEGIN(prof); mbar_wait_relaxed(b.wempty + 8 * s, ph ^ 1u); TC_PROF_END(prof, st); }
                     if (rank == 0) mbar_expect_tx(b.wfull + 8 * s, 2u * row_bytes);
-                    tma_load_2d_pair(smem_u32(ring) + s * row_bytes, &tmap_w, lead_wfull + 8 * s, 0, (slab0 + it * p.kw) * p.pair_split);
+                    tma_load_2d_pair(smem_u32(ring) + s * row_bytes, &tmap_w, lead_wfull + 8 * s, 0, (slab0 + it * p.kws) * p.pair_split);
                     if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -955,12 +966,12 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             const int m = warp - 2;
             const uint32_t aa = smem_u32(act), ra = smem_u32(ring);
             if (p.stacked) {
-                if (p.kw == 3) pair_issuer<3, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
-                else if (p.kw == 5) pair_issuer<5, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
+                if (p.kws == 3) pair_issuer<3, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
+                else if (p.kws == 5) pair_issuer<5, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
                 else pair_issuer<1, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
             } else {
-                if (p.kw == 3) pair_issuer<3, false>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
-                else if (p.kw == 5) pair_issuer<5, false>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
+                if (p.kws == 3) pair_issuer<3, false>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
+                else if (p.kws == 5) pair_issuer<5, false>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
                 else pair_issuer<1, false>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
             }
         }
@@ -1051,7 +1062,9 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     if (B <= 0) return PMP_OK;
     TcGeom g;
     const int H = a.Ho ? a.Ho : a.in.H, W = a.in.W, Hin = a.in.H;
-    const bool want_pair = tc_pair_default() && B >= 2 && a.w_pair;
+    // (a batch of one runs the pair kernel too: the peer CTA recomputes the image and drops it -- one arithmetic for
+    // every batch composition; the single-CTA kernel remains as the PMP_TC_PAIR=0 / self-test A-B path)
+    const bool want_pair = tc_pair_default() && a.w_pair;
     bool geom_ok = want_pair && tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g, -1, true) &&
                    (g.stacked != 0) == tc_pair_stacked_layout(a.cout_pad, a.kh, a.kw);
     const bool use_pair = geom_ok;
@@ -1110,9 +1123,13 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         // (slabs above 2 KB = 256 elements -- stacked Cout = 64: 3 KB -- take two map rows, one per k8 half)
         const uint32_t slab = 32u * (uint32_t)tc_pair_slab_rows(g.coutp, a.kh, a.kw);
         const uint32_t split = slab > 2048u ? 2u : 1u;
+        // a ring stage is a whole filter row unless fewer than 4 such stages fit beside the activation tile (5x5 layers
+        // with 3 KB slabs): then single taps
+        tc_ring_layout(g, slab * (uint32_t)a.kw, a.kh);
+        const int kws = (g.nstages >= 4 || a.kw == 1) ? a.kw : 1;
         cuuint64_t wdim[2] = {slab / split / 8, nslab * split};
         cuuint64_t wstr[1] = {slab / split};
-        cuuint32_t wbox[2] = {slab / split / 8, (cuuint32_t)a.kw * split};
+        cuuint32_t wbox[2] = {slab / split / 8, (cuuint32_t)kws * split};
         cuuint32_t west[2] = {1, 1};
         cr = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void *)a.w_pair, wdim, wstr, wbox, west,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1131,17 +1148,23 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         p.nslot = 512 / p.acc_cols < 8 ? 512 / p.acc_cols : 8;
         p.mt_alloc = p.nslot < 8 ? 3 : 4;
         p.tmem_cols = g.tmem_cols;
-        tc_ring_layout(g, slab * (uint32_t)a.kw, a.kh);           // ring stages are filter rows
-        p.nstages = g.nstages; p.nbuf = g.nbuf;
+        tc_ring_layout(g, slab * (uint32_t)kws, a.kh * (a.kw / kws));
+        p.nstages = g.nstages; p.nbuf = g.nbuf; p.kws = kws;
         const uint32_t smem_pair = g.smem_bytes;
         p.idesc1 = idesc_base_nom | ((uint32_t)(g.coutp >> 3) << 17) | ((256u >> 4) << 24);      // M = 256 across the pair
         p.idesc2 = idesc_base_nom | ((uint32_t)(g.N1 >> 3) << 17) | ((256u >> 4) << 24);         // stacked: N = 2*Cout
         int nsm = h->num_sms & ~1;
         int grid = 2 * p.pair_items < nsm ? 2 * p.pair_items : nsm;
         ProfScope ps(h, PROF_CONV_TC, s, flops, 0);
-        conv_tc_pair_kernel<<<grid, TC_THREADS, smem_pair, s>>>(tmap, tmap_w, p);
+        static const int env_pdl = [] { const char *e = getenv("PMP_TC_PDL"); return e ? atoi(e) : 1; }();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem_pair; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = env_pdl ? 1 : 0;
+        PMP_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, tmap, tmap_w, p));
         h->launches++;
-        PMP_CUDA(cudaGetLastError());
         return PMP_OK;
     }
     dim3 grid(p.items < h->num_sms ? p.items : h->num_sms);
@@ -1299,7 +1322,7 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     struct KnobReset {      // the variant knobs are process-wide: restore the defaults on every exit path
         ~KnobReset() { pmp::g_tc_scheme = -1; pmp::g_tc_pair = -1; pmp::g_tc_nbuf_max = -1; pmp::g_tc_st64 = -1; }
     } knob_reset;
-    pmp::g_tc_st64 = (flags >> 12) & 1 ? 0 : -1;         // bit 12: unstacked accumulators for the 3x3 Cout = 64 layers (A/B)
+    pmp::g_tc_st64 = (flags >> 12) & 1 ? 0 : -1;         // bit 12: unstacked accumulators for the Cout = 64 layers (A/B)
     const int cinp = pad16(cin), coutp = pad16(cout);
     if (!tc_supported(cinp, coutp, ksize, ksize, H, W)) {
         set_error("selftest: configuration not supported by the TC engine");

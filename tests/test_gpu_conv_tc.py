@@ -33,7 +33,10 @@ VARIANTS = [((64, 64, 3, 32, 5, 3), 1 << 11), ((64, 64, 3, 32, 5, 3), 1 << 10), 
             # 3x3 Cout = 64: default stacked scheme on the 4-slot accumulator ring vs the unstacked A/B variant (bit 12),
             # enough tiles per cluster to wrap the slot ring and the weight ring many times
             ((64, 64, 3, 64, 150, 3), 1 << 10), ((64, 64, 3, 64, 150, 3), (1 << 10) | (1 << 12)), ((64, 64, 3, 32, 333, 7), 1 << 10),
-            ((64, 64, 3, 16, 75, 7), 1 << 10), ((32, 64, 3, 32, 5, 1), 1 << 11)]
+            ((64, 64, 3, 16, 75, 7), 1 << 10), ((32, 64, 3, 32, 5, 1), 1 << 11),
+            # 5x5 Cout = 64: stacked with single-tap ring stages (default) vs unstacked row stages (bit 12)
+            ((64, 64, 5, 64, 150, 3), 1 << 10), ((64, 64, 5, 64, 150, 3), (1 << 10) | (1 << 12)), ((32, 64, 5, 64, 77, 1), 1 << 10),
+            ((64, 64, 5, 32, 333, 3), 1 << 10), ((32, 64, 5, 32, 200, 1), 1 << 10), ((64, 64, 5, 64, 3, 1), 1 << 11)]
 
 
 @pytest.mark.parametrize("cfg,mode", VARIANTS, ids=lambda v: str(v).replace(" ", ""))

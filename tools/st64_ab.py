@@ -3,7 +3,7 @@ import ctypes, sys
 sys.path.insert(0, ".")
 from pmp_vvc_tip2023_b200 import _lib
 h = _lib.Handle.get(0); L = _lib.lib()
-for cin, cout, k, hw, b, fl in [(64, 64, 3, 64, 592, 1), (64, 64, 3, 64, 592, 3), (64, 64, 3, 32, 2400, 1), (64, 64, 3, 32, 2400, 3), (64, 64, 3, 32, 2400, 7), (32, 64, 3, 32, 2400, 1), (64, 64, 3, 16, 2400, 7), (32, 64, 3, 16, 2400, 1)]:
+for cin, cout, k, hw, b, fl in [(64, 64, 5, 64, 592, 3), (32, 64, 5, 64, 592, 1), (64, 64, 5, 32, 2400, 1), (64, 64, 5, 32, 2400, 3), (32, 64, 5, 32, 2400, 1), (64, 64, 3, 64, 592, 1), (64, 64, 3, 64, 592, 3), (64, 64, 3, 32, 2400, 1), (64, 64, 3, 32, 2400, 3), (64, 64, 3, 32, 2400, 7), (32, 64, 3, 32, 2400, 1), (64, 64, 3, 16, 2400, 7), (32, 64, 3, 16, 2400, 1)]:
     for name, bit in (("stacked  ", 0), ("unstacked", 1 << 12)):
         me, am, t1, t2 = (ctypes.c_double() for _ in range(4))
         rc = L.pmp_selftest_conv(h.ptr, cin, cout, k, hw, b, fl | bit, ctypes.byref(me), ctypes.byref(am), ctypes.byref(t1), ctypes.byref(t2))
