@@ -196,8 +196,24 @@ size_t tc_pair_packed_elems(int cin_pad, int cout_pad, int kh, int kw)
 
 void pack_tc_pair_weights(const float *w, int cout, int cin, int kh, int kw, int cin_pad, int cout_pad, bool bf16, uint16_t *dst)
 {
-    const int groups = cin_pad / 16, taps = kh * kw, half = cout_pad / 2, rows = tc_pair_slab_rows(cout_pad, kh, kw);
-    const bool st = tc_pair_stacked_layout(cout_pad, kh, kw);
+    pack_tc_pair_weights_scheme(w, cout, cin, kh, kw, cin_pad, cout_pad, bf16, tc_pair_stacked_layout(cout_pad, kh, kw), dst);
+}
+
+// 1x1 shortcut conv fused into a kh x kw conv with the same Cout: its slabs use the HOST conv's accumulator scheme
+size_t tc_pair_fused_sc_elems(int sc_cin_pad, int cout_pad, int kh, int kw)
+{
+    return (size_t)2 * (sc_cin_pad / 16) * 2 * tc_pair_slab_rows(cout_pad, kh, kw) * 8;
+}
+void pack_tc_pair_fused_sc(const float *w_sc, int cout, int sc_cin, int sc_cin_pad, int cout_pad, int kh, int kw, bool bf16, uint16_t *dst)
+{
+    pack_tc_pair_weights_scheme(w_sc, cout, sc_cin, 1, 1, sc_cin_pad, cout_pad, bf16, tc_pair_stacked_layout(cout_pad, kh, kw), dst);
+}
+bool tc_fusion_available() { return tc_pair_default(); }
+
+void pack_tc_pair_weights_scheme(const float *w, int cout, int cin, int kh, int kw, int cin_pad, int cout_pad, bool bf16, bool st,
+                                 uint16_t *dst)
+{
+    const int groups = cin_pad / 16, taps = kh * kw, half = cout_pad / 2, rows = st ? cout_pad + cout_pad / 2 : cout_pad;
     auto weight = [&](int co, int c, int t, uint16_t &hi, uint16_t &lo) {
         hi = lo = 0;
         if (co < cout && c < cin) host_split(w[((size_t)co * cin + c) * taps + t], bf16, hi, lo);
@@ -267,13 +283,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tma
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
-// L2 prefetch of a TMA box (no shared-memory destination): issued one tile ahead so that the box load itself hits L2 --
-// per-SM TMA throughput on HBM-resident data is bounded by the requests the SM can keep in flight over the DRAM latency
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *tmap, int c0, int c1, int c2, int c3)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
-                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -335,8 +344,9 @@ struct TcParams {
     Act out, res, mul;
     int H, W, P, kh, kw, pady, padx, groups, total_mt, tiles, N1, coutp, nstages, items;
     uint32_t plane_bytes, group_bytes, stage_bytes, tmem_cols, idesc1, idesc2;
-    int relu, stacked, pairbuf, nbuf, dbg, prefetch;
+    int relu, stacked, pairbuf, nbuf, dbg;
     int nslot, mt_alloc, acc_cols;      // CTA-pair kernel: accumulator slot ring (slots, M-tiles per tile, columns per slot)
+    int aslots, groups2;                // CTA-pair kernel: activation slot ring (one channel-group box each); fused shortcut groups
     int B, pair_items;      // CTA-pair kernel: images in the batch, work items = tiles * ceil(B/2)
     uint32_t pair_slab;     // CTA-pair kernel: bytes of one per-CTA weight slab
     int pair_split;         // CTA-pair kernel: rows of the weight tensor map per slab (1, or 2 for 3 KB slabs)
@@ -541,10 +551,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
             uint32_t ab = 0, aph = 0;                 // activation buffer of this item, parity of its use count
             for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
                 const TileGeom t = tile_geom(p, item);
-                if (p.prefetch && item + p.prefetch * (int)gridDim.x < p.items) {
-                    const TileGeom tn = tile_geom(p, item + p.prefetch * (int)gridDim.x);
-                    for (int g = 0; g < p.groups; g++) tma_prefetch_4d(&tmap, -2 * p.padx, tn.row0 - p.pady, g * 4, tn.n);
-                }
                 for (int g = 0; g < p.groups; g++) {
                     const uint32_t slot = ab * (uint32_t)p.groups + (uint32_t)g;
                     mbar_wait_relaxed(bar_aempty + 8 * slot, aph ^ 1u);
@@ -812,7 +818,9 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
     const uint32_t peer_wempty = mapa_cluster(b.wempty, 1), peer_aempty = mapa_cluster(b.aempty, 1), peer_acc = mapa_cluster(b.acc, 1);
     const int KH = p.kh, P = p.P, NS = p.nstages, G = p.groups;
     long long st_a = 0, st_b = 0, st_c = 0;
-    uint32_t s = 0, ph = 0, idx = 0, ab = 0, aph = 0;
+    const int G2 = p.groups2;                    // fused 1x1 shortcut: extra channel groups of a second input, centre tap only
+    const uint32_t ASLOTS = (uint32_t)p.aslots, ctr16 = (uint32_t)(p.pady * p.P + p.padx);
+    uint32_t s = 0, ph = 0, idx = 0, as = 0, aph = 0;   // weight stage / activation slot of the ring and their parities
     for (int item = cid; item < p.pair_items; item += ncl, idx++) {
         const PairGeom t = pair_geom(p, item, 0);
         const bool mine = m < t.mt_count;
@@ -825,9 +833,8 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
         }
         uint32_t acc = 0;
         for (int g = 0; g < G; g++) {
-            const uint32_t slot = ab * (uint32_t)G + (uint32_t)g;
-            { TC_PROF_BEGIN(prof); mbar_wait(b.afull + 8 * slot, aph); TC_PROF_END(prof, st_b); }
-            uint32_t arow = act16 + slot * group16 + (uint32_t)t.qoff;
+            { TC_PROF_BEGIN(prof); mbar_wait(b.afull + 8 * as, aph); TC_PROF_END(prof, st_b); }
+            uint32_t arow = act16 + as * group16 + (uint32_t)t.qoff;
             for (int kr = 0, sx = 0; kr < KH * RS; kr++) {
                 { TC_PROF_BEGIN(prof); mbar_wait(b.wfull + 8 * s, ph); TC_PROF_END(prof, st_c); }
                 tc_fence_after();
@@ -859,10 +866,38 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
                 if (++sx == RS) { sx = 0; arow += (uint32_t)P; }
             }
             if (elect_one_sync()) {                              // activation buffer free for a later tile
-                if (mine) umma_commit_pair(b.aempty + 8 * slot);
-                else { mbar_arrive(b.aempty + 8 * slot); mbar_arrive_cluster_relaxed(peer_aempty + 8 * slot); }
+                if (mine) umma_commit_pair(b.aempty + 8 * as);
+                else { mbar_arrive(b.aempty + 8 * as); mbar_arrive_cluster_relaxed(peer_aempty + 8 * as); }
             }
             __syncwarp();
+            if (++as == ASLOTS) { as = 0; aph ^= 1u; }
+        }
+        for (int g = 0; g < G2; g++) {           // out += W_sc * x: one slab per group, A = the tile's own positions
+            { TC_PROF_BEGIN(prof); mbar_wait(b.afull + 8 * as, aph); TC_PROF_END(prof, st_b); }
+            { TC_PROF_BEGIN(prof); mbar_wait(b.wfull + 8 * s, ph); TC_PROF_END(prof, st_c); }
+            tc_fence_after();
+            const uint64_t ad = adesc_c | (uint64_t)(act16 + as * group16 + (uint32_t)t.qoff + ctr16);
+            const uint64_t bd = bdesc_c | (uint64_t)(ring16 + s * row16);
+            if (elect_one_sync()) {
+                if (mine) {
+                    if (ST) {
+                        umma_f16_pair(d_tmem, ad, bd, idesc_st, 1u);
+                        umma_f16_pair(d_tmem, ad + lo16, bd + wlo16, idesc, 1u);
+                    } else {
+                        umma_f16_pair(d_tmem, ad, bd, idesc, 1u);
+                        umma_f16_pair(d_tmem, ad, bd + wlo16, idesc, 1u);
+                        umma_f16_pair(d_tmem, ad + lo16, bd, idesc, 1u);
+                    }
+                    umma_commit_pair(b.wempty + 8 * s);
+                    umma_commit_pair(b.aempty + 8 * as);
+                } else {
+                    mbar_arrive(b.wempty + 8 * s); mbar_arrive_cluster_relaxed(peer_wempty + 8 * s);
+                    mbar_arrive(b.aempty + 8 * as); mbar_arrive_cluster_relaxed(peer_aempty + 8 * as);
+                }
+            }
+            __syncwarp();
+            if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
+            if (++as == ASLOTS) { as = 0; aph ^= 1u; }
         }
         if (has_slot) {
             if (elect_one_sync()) {                              // this M-tile's accumulator is complete
@@ -873,7 +908,6 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
             slot += MTA;
             if (slot >= NSLOT) { slot -= NSLOT; sph ^= 1u; }
         }
-        if (++ab == (uint32_t)p.nbuf) { ab = 0; aph ^= 1u; }
     }
     if (prof && m == 0 && (threadIdx.x & 31) == 0) {
         unsigned long long *o = g_tc_stalls + blockIdx.x * TC_PROF_SLOTS;
@@ -882,7 +916,8 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap2, const __grid_constant__ CUtensorMap tmap_w2, const TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
@@ -892,7 +927,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     b.wempty = smem_u32(bars + 56); b.acc = smem_u32(bars + 80); b.accempty = smem_u32(bars + 88);     // 8 + 8 accumulator slots
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 1008);
     uint8_t *act = smem + TC_SMEM_HEADER;
-    uint8_t *ring = act + (size_t)p.nbuf * p.groups * p.group_bytes;
+    uint8_t *ring = act + (size_t)p.aslots * p.group_bytes;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
@@ -902,7 +937,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     const long long t_begin = prof ? clock64() : 0;
 
     if (threadIdx.x == 0) {
-        for (int g = 0; g < p.nbuf * p.groups; g++) { mbar_init(b.afull + 8 * g, 1); mbar_init(b.aempty + 8 * g, TC_MMA_WARPS); }
+        for (int g = 0; g < p.aslots; g++) { mbar_init(b.afull + 8 * g, 1); mbar_init(b.aempty + 8 * g, TC_MMA_WARPS); }
         for (int s = 0; s < p.nstages; s++) { mbar_init(b.wfull + 8 * s, 1); mbar_init(b.wempty + 8 * s, TC_MMA_WARPS); }
         for (int m = 0; m < p.nslot; m++) { mbar_init(b.acc + 8 * m, 1); mbar_init(b.accempty + 8 * m, 2 * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -938,6 +973,13 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     tma_load_2d_pair(smem_u32(ring) + s * row_bytes, &tmap_w, lead_wfull + 8 * s, 0, (slab0 + it * p.kws) * p.pair_split);
                     if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1u; }
                 }
+                for (int g2 = 0; g2 < p.groups2; g2++) {         // fused shortcut: one slab per group of the second input
+                    { TC_PROF_BEGIN(prof); mbar_wait_relaxed(b.wempty + 8 * s, ph ^ 1u); TC_PROF_END(prof, st); }
+                    if (rank == 0) mbar_expect_tx(b.wfull + 8 * s, 2u * p.pair_slab);
+                    tma_load_2d_pair(smem_u32(ring) + s * row_bytes, &tmap_w2, lead_wfull + 8 * s, 0,
+                                     ((int)rank * p.groups2 + g2) * p.pair_split);
+                    if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1u; }
+                }
             }
             if (prof) g_tc_stalls[blockIdx.x * TC_PROF_SLOTS + 4] = st;
         }
@@ -946,17 +988,18 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             // ===== activation producer (own image), bytes counted on the leader's act_full =====
             const uint32_t lead_afull = mapa_cluster(b.afull, 0);
             long long st = 0;
-            uint32_t ab = 0, aph = 0;
+            uint32_t as = 0, aph = 0;
+            const int V = p.groups + p.groups2;             // channel groups of the input, then of the fused shortcut's input
             for (int item = cid; item < p.pair_items; item += ncl) {
                 const PairGeom t = pair_geom(p, item, (int)rank);
-                for (int g = 0; g < p.groups; g++) {
-                    const uint32_t slot = ab * (uint32_t)p.groups + (uint32_t)g;
-                    { TC_PROF_BEGIN(prof); mbar_wait_relaxed(b.aempty + 8 * slot, aph ^ 1u); TC_PROF_END(prof, st); }
-                    if (rank == 0) mbar_expect_tx(b.afull + 8 * slot, 2u * p.group_bytes);
-                    tma_load_4d_pair(smem_u32(act + (size_t)slot * p.group_bytes), &tmap, lead_afull + 8 * slot, -2 * p.padx,
-                                     t.row0 - p.pady, g * 4, t.n);
+                for (int v = 0; v < V; v++) {
+                    { TC_PROF_BEGIN(prof); mbar_wait_relaxed(b.aempty + 8 * as, aph ^ 1u); TC_PROF_END(prof, st); }
+                    if (rank == 0) mbar_expect_tx(b.afull + 8 * as, 2u * p.group_bytes);
+                    const bool second = v >= p.groups;
+                    tma_load_4d_pair(smem_u32(act + (size_t)as * p.group_bytes), second ? &tmap2 : &tmap, lead_afull + 8 * as,
+                                     -2 * p.padx, t.row0 - p.pady, (second ? v - p.groups : v) * 4, t.n);
+                    if (++as == (uint32_t)p.aslots) { as = 0; aph ^= 1u; }
                 }
-                if (++ab == (uint32_t)p.nbuf) { ab = 0; aph ^= 1u; }
             }
             if (prof) g_tc_stalls[blockIdx.x * TC_PROF_SLOTS + 5] = st;
         }
@@ -1107,14 +1150,18 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     p.relu = a.relu; p.stacked = g.stacked; p.pairbuf = g.pairbuf; p.nbuf = g.nbuf;
     static const int env_dbg = [] { const char *e = getenv("PMP_TC_DBG"); return e ? atoi(e) : 0; }();   // timing experiments only
     p.dbg = env_dbg;
-    static const int env_pf = [] { const char *e = getenv("PMP_TC_PREFETCH"); return e ? atoi(e) : 1; }();   // tiles of L2 prefetch distance
-    p.prefetch = env_pf;
     if (!h->tc_attr_set) {          // function attributes are per device: one handle per device
         PMP_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
         PMP_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
         h->tc_attr_set = true;
     }
-    const double flops = a.flops_override > 0 ? a.flops_override * B : 2.0 * B * H * W * (double)a.out.C * a.in.C * a.kh * a.kw;
+    const double flops = a.flops_override > 0 ? a.flops_override * B
+                                               : 2.0 * B * H * W * (double)a.out.C * ((double)a.in.C * a.kh * a.kw + (a.sc_in.p ? a.sc_in.C : 0));
+    if (a.sc_in.p && (!use_pair || !a.w_pair_sc || a.sc_in.fmt != FMT_SPLIT || a.sc_in.H != Hin || a.sc_in.W != W ||
+                      a.sc_in.Cp != a.sc_cin_pad || a.sc_cin_pad % 16 || a.res.p)) {
+        set_error("conv_tc: fused shortcut needs the CTA-pair kernel, a split-format second input of the same size and no residual");
+        return PMP_ERR_UNSUPPORTED;
+    }
     if (use_pair) {
         // CTA-pair kernel: 2-D tensor map over this conv's per-CTA weight slabs (8-byte elements, one slab per map row);
         // one box = one filter row of one channel group = kw consecutive slabs = one ring stage
@@ -1138,6 +1185,27 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
             set_error("cuTensorMapEncodeTiled (pair weights) failed (%d)", (int)cr);
             return PMP_ERR_CUDA;
         }
+        // fused 1x1 shortcut: second activation tensor (same box) and its own one-slab-per-group weight map
+        CUtensorMap tmap2 = tmap, tmap_w2 = tmap_w;
+        p.groups2 = 0;
+        if (a.sc_in.p) {
+            const cuuint64_t planes2 = (cuuint64_t)a.sc_cin_pad / 4;
+            cuuint64_t gdim2[4] = {(cuuint64_t)W * 2, (cuuint64_t)Hin, planes2, (cuuint64_t)B};
+            cuuint64_t gstr2[3] = {(cuuint64_t)W * 16, (cuuint64_t)Hin * W * 16, planes2 * Hin * W * 16};
+            cr = enc(&tmap2, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, a.sc_in.p, gdim2, gstr2, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            p.groups2 = a.sc_cin_pad / 16;
+            cuuint64_t wdim2[2] = {slab / split / 8, (cuuint64_t)2 * p.groups2 * split};
+            cuuint32_t wbox2[2] = {slab / split / 8, split};
+            if (cr == CUDA_SUCCESS)
+                cr = enc(&tmap_w2, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void *)a.w_pair_sc, wdim2, wstr, wbox2, west,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) {
+                set_error("cuTensorMapEncodeTiled (fused shortcut) failed (%d)", (int)cr);
+                return PMP_ERR_CUDA;
+            }
+        }
         p.B = B;
         p.pair_items = g.tiles * ((B + 1) / 2);
         p.pairbuf = 0; p.pair_slab = slab; p.pair_split = (int)split;
@@ -1150,7 +1218,22 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         p.tmem_cols = g.tmem_cols;
         tc_ring_layout(g, slab * (uint32_t)kws, a.kh * (a.kw / kws));
         p.nstages = g.nstages; p.nbuf = g.nbuf; p.kws = kws;
-        const uint32_t smem_pair = g.smem_bytes;
+        p.aslots = g.nbuf * g.groups;           // activation ring: one slot per channel-group box, any number of them
+        uint32_t smem_pair = g.smem_bytes;
+        if (p.groups2) {
+            // the input's and the shortcut input's groups cycle through the slots; take what fits beside a useful ring
+            int want = g.groups * a.kh * (a.kw / kws) + p.groups2;
+            if (want > TC_MAX_STAGES) want = TC_MAX_STAGES;
+            if (want > g.nstages) want = g.nstages;
+            int slots = (int)((TC_SMEM_MAX - TC_SMEM_HEADER - (uint32_t)want * slab * (uint32_t)kws) / g.group_bytes);
+            if (slots > 16) slots = 16;
+            if (slots > 4 * (g.groups + p.groups2)) slots = 4 * (g.groups + p.groups2);
+            if (slots < g.groups) slots = g.groups;
+            p.aslots = slots;
+            int ns = (int)((TC_SMEM_MAX - TC_SMEM_HEADER - (uint32_t)slots * g.group_bytes) / (slab * (uint32_t)kws));
+            p.nstages = ns < TC_MAX_STAGES ? ns : TC_MAX_STAGES;
+            smem_pair = TC_SMEM_HEADER + (uint32_t)slots * g.group_bytes + (uint32_t)p.nstages * slab * (uint32_t)kws;
+        }
         p.idesc1 = idesc_base_nom | ((uint32_t)(g.coutp >> 3) << 17) | ((256u >> 4) << 24);      // M = 256 across the pair
         p.idesc2 = idesc_base_nom | ((uint32_t)(g.N1 >> 3) << 17) | ((256u >> 4) << 24);         // stacked: N = 2*Cout
         int nsm = h->num_sms & ~1;
@@ -1163,7 +1246,7 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = env_pdl ? 1 : 0;
-        PMP_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, tmap, tmap_w, p));
+        PMP_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, tmap, tmap_w, tmap2, tmap_w2, p));
         h->launches++;
         return PMP_OK;
     }
@@ -1341,6 +1424,11 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     for (auto &v : hmul) v = 1.5f * lcg(seed);
 
     DevBuf d_in32, d_res32, d_mul32, d_in, d_res, d_mul, d_out, d_out32, d_ref32, d_wsimt, d_wtc, d_wpair;
+    // bit 17: fused 1x1 shortcut on a second input with ((flags >> 20) & 0xff, default 32) channels (excludes bit 1)
+    const bool fused = (flags >> 17) & 1;
+    const int cin2 = fused ? (((flags >> 20) & 0xff) ? ((flags >> 20) & 0xff) : 32) : 0, cin2p = pad16(cin2);
+    DevBuf d_in2_32, d_in2, d_sc32, d_wsimt2, d_wsc;
+    if (fused && (flags & 2)) { set_error("selftest: fused shortcut excludes the identity residual"); return PMP_ERR_ARG; }
     const size_t sp_in = act_bytes(FMT_SPLIT, B, cin, H, W), sp_out = act_bytes(FMT_SPLIT, B, cout, H, W);
     if (d_in32.alloc(n_in * 4) || d_res32.alloc(n_out * 4) || d_mul32.alloc(n_out * 4) || d_in.alloc(sp_in) ||
         d_res.alloc(sp_out) || d_mul.alloc(sp_out) || d_out.alloc(sp_out) || d_out32.alloc(n_out * 4) ||
@@ -1378,6 +1466,25 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
         PMP_CUDA(cudaMemcpy(d_wpair.p, pp.data(), pp.size() * 2, cudaMemcpyHostToDevice));
     }
 
+    if (fused) {
+        const size_t u2 = (size_t)Bu * cin2 * H * W, n2 = (size_t)B * cin2 * H * W;
+        std::vector<float> hin2(u2), hw2((size_t)cout * cin2);
+        for (auto &v : hin2) v = 30.f * fabsf(lcg(seed)) * (lcg(seed) > -0.2f ? 1.f : 0.f);
+        const float wb2 = sqrtf(3.0f / cin2);
+        for (auto &v : hw2) v = wb2 * lcg(seed);
+        std::vector<float> ps2((size_t)cin2 * coutw, 0.f);
+        for (int o = 0; o < cout; o++)
+            for (int c = 0; c < cin2; c++) ps2[(size_t)c * coutw + o] = hw2[(size_t)o * cin2 + c];
+        std::vector<uint16_t> pf(tc_pair_fused_sc_elems(cin2p, coutp, ksize, ksize));
+        pack_tc_pair_fused_sc(hw2.data(), cout, cin2, cin2p, coutp, ksize, ksize, bf, pf.data());
+        if (d_in2_32.alloc(n2 * 4) || d_in2.alloc(act_bytes(FMT_SPLIT, B, cin2, H, W)) || d_sc32.alloc(n_out * 4) ||
+            d_wsimt2.alloc(ps2.size() * 4) || d_wsc.alloc(pf.size() * 2))
+            return PMP_ERR_CUDA;
+        PMP_CUDA(upload_tiled(d_in2_32.p, hin2, n2));
+        PMP_CUDA(cudaMemcpy(d_wsimt2.p, ps2.data(), ps2.size() * 4, cudaMemcpyHostToDevice));
+        PMP_CUDA(cudaMemcpy(d_wsc.p, pf.data(), pf.size() * 2, cudaMemcpyHostToDevice));
+    }
+
     auto mk = [&](void *p, int C) {
         Act a;
         a.p = p; a.fmt = FMT_SPLIT; a.C = C; a.Cp = pad16(C); a.H = H; a.W = W; a.bf16 = bf;
@@ -1389,6 +1496,8 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     f32_to_split_kernel<<<1024, 256, 0, s>>>((const float *)d_res32.p, res, B);
     f32_to_split_kernel<<<1024, 256, 0, s>>>((const float *)d_mul32.p, mul, B);
     PMP_CUDA(cudaMemsetAsync(d_out.p, 0xFF, sp_out, s));
+    Act in2 = mk(d_in2.p, cin2);
+    if (fused) f32_to_split_kernel<<<1024, 256, 0, s>>>((const float *)d_in2_32.p, in2, B);
     PMP_CUDA(cudaGetLastError());
 
     cudaEvent_t e0, e1, e2, e3;
@@ -1401,8 +1510,19 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     if (flags & 4) sa.mul = mul;
     sa.w = (const float *)d_wsimt.p; sa.cin = cin; sa.cout = cout; sa.coutw = coutw;
     sa.pad_t = sa.pad_l = ksize / 2; sa.Ho = H; sa.Wo = W; sa.relu = flags & 1; sa.pool = 1;
+    int rc = PMP_OK;
+    if (fused) {            // reference: exact fp32 1x1 conv of the second input, added as the residual of the main conv
+        SimtConvArgs sc;
+        sc.in = in2;
+        sc.out.p = d_sc32.p; sc.out.fmt = FMT_F32; sc.out.C = sc.out.Cp = cout; sc.out.H = H; sc.out.W = W;
+        sc.w = (const float *)d_wsimt2.p; sc.cin = cin2; sc.cout = cout; sc.coutw = coutw;
+        sc.pad_t = sc.pad_l = 0; sc.Ho = H; sc.Wo = W; sc.relu = 0; sc.pool = 1;
+        rc = conv_simt(h, sc, 1, 1, B, s);
+        if (rc) return rc;
+        sa.res = sc.out;
+    }
     cudaEventRecord(e0, s);
-    int rc = conv_simt(h, sa, ksize, ksize, B, s);
+    rc = conv_simt(h, sa, ksize, ksize, B, s);
     cudaEventRecord(e1, s);
     if (rc) return rc;
     TcConvArgs ta;
@@ -1410,6 +1530,7 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     if (flags & 2) ta.res = res;
     if (flags & 4) ta.mul = mul;
     ta.w = (const uint16_t *)d_wtc.p; ta.w_pair = (const uint16_t *)d_wpair.p; ta.cin_pad = cinp; ta.cout_pad = coutp; ta.kh = ta.kw = ksize; ta.pad_t = ta.pad_l = ksize / 2; ta.relu = flags & 1; ta.pool = 1;
+    if (fused) { ta.sc_in = in2; ta.w_pair_sc = (const uint16_t *)d_wsc.p; ta.sc_cin_pad = cin2p; }
     pmp::g_tc_scheme = ((flags >> 8) & 3) - 1;          // 0: library default, 1: unstacked, 2: stacked
     pmp::g_tc_pair = (flags >> 10) & 1 ? 1 : ((flags >> 11) & 1 ? 0 : -1);   // bit 10: CTA-pair kernel, bit 11: force single
     pmp::g_tc_nbuf_max = ((flags >> 13) & 7) ? ((flags >> 13) & 7) : -1;      // bits 13..15: cap on activation buffers (0: default)

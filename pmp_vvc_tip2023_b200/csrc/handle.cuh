@@ -15,6 +15,9 @@ struct ConvW {
     uint16_t *w_tc_bf16 = nullptr;
     uint16_t *w_pair_f16 = nullptr, *w_pair_bf16 = nullptr;   // CTA-pair kernel images
     int cin_pad = 0, cout_pad = 0;      // channel counts padded to multiples of 16
+    // second conv of a ResidualBlock with a 1x1 shortcut: the shortcut's weights packed for fusion into this conv
+    uint16_t *w_pair_sc_f16 = nullptr, *w_pair_sc_bf16 = nullptr;
+    int sc_cin = 0, sc_cin_pad = 0;
 };
 
 struct WeightSet {

@@ -34,6 +34,11 @@ struct TcConvArgs {
     const uint16_t *w = nullptr;    // packed main weights (see pack_tc_weights)
     const uint16_t *w_pair = nullptr;   // CTA-pair operand image or nullptr
     const float *bias = nullptr;    // [cout_pad] fp32 or nullptr (stems only)
+    // fused 1x1 shortcut (ResidualBlock with Cin != Cout, Model_QBD.py:34-38,43): out = epilogue(conv(in) + W_sc * sc_in);
+    // sc_in has the conv's H x W, w_pair_sc is packed by pack_tc_pair_fused_sc.  CTA-pair kernel only, excludes `res`.
+    Act sc_in;
+    const uint16_t *w_pair_sc = nullptr;
+    int sc_cin_pad = 0;
     int cin_pad = 0, cout_pad = 0, kh = 1, kw = 1;
     int pad_t = 0, pad_l = 0;       // input coordinate = output coordinate + tap - pad
     int Ho = 0;                     // output rows (0: same as the input)
@@ -47,6 +52,11 @@ size_t tc_packed_elems(int cin_pad, int cout_pad, int kh, int kw);
 void pack_tc_weights(const float *w, int cout, int cin, int kh, int kw, int cin_pad, int cout_pad, bool bf16, uint16_t *dst);
 size_t tc_pair_packed_elems(int cin_pad, int cout_pad, int kh, int kw);
 void pack_tc_pair_weights(const float *w, int cout, int cin, int kh, int kw, int cin_pad, int cout_pad, bool bf16, uint16_t *dst);
+void pack_tc_pair_weights_scheme(const float *w, int cout, int cin, int kh, int kw, int cin_pad, int cout_pad, bool bf16, bool st,
+                                 uint16_t *dst);
+size_t tc_pair_fused_sc_elems(int sc_cin_pad, int cout_pad, int kh, int kw);
+void pack_tc_pair_fused_sc(const float *w_sc, int cout, int sc_cin, int sc_cin_pad, int cout_pad, int kh, int kw, bool bf16, uint16_t *dst);
+bool tc_fusion_available();      // the CTA-pair kernel is the active TC path (fused shortcuts need it)
 // U[c*kw + j][y][x] = X[c][y][x + j] (x2 = cat[x, pad_lu(up(qt))] when qt != nullptr): the kx taps of a first-layer conv
 // unrolled into channels so that the tensor-core kernel can run it as a kh x 1 conv.  out: FMT_SPLIT [B, (cx+1?)*kw, S0, S1]
 int stem_unroll(Handle *h, const Act &x, const float *qt, int up, int ov, int kw, const Act &out, int B, cudaStream_t s);

@@ -200,6 +200,24 @@ int weights_create(Handle *h, int net, const float *const *tensors, const int64_
             }
         }
     }
+    // 1x1 shortcuts (Model_QBD.py:34-38) packed for fusion into the second conv of their block (conv_tc.cu, TcConvArgs::sc_in)
+    for (int i = 0; i < n && rc == PMP_OK; i++) {
+        const std::string &nm = spec[i].name;
+        const std::string tail = ".shortcut.0.weight";
+        if (nm.size() <= tail.size() || nm.compare(nm.size() - tail.size(), tail.size(), tail) != 0) continue;
+        auto it = ws.convs.find(nm.substr(0, nm.size() - tail.size()) + ".left.2");
+        if (it == ws.convs.end() || !it->second.w_pair_f16) continue;
+        ConvW &l2 = it->second;
+        const int co = spec[i].d[0], ci = spec[i].d[1];
+        if (co != l2.cout) continue;
+        l2.sc_cin = ci; l2.sc_cin_pad = pad16(ci);
+        std::vector<uint16_t> pf(tc_pair_fused_sc_elems(l2.sc_cin_pad, l2.cout_pad, l2.kh, l2.kw));
+        pack_tc_pair_fused_sc(tensors[i], co, ci, l2.sc_cin_pad, l2.cout_pad, l2.kh, l2.kw, false, pf.data());
+        rc = dev_upload(ws, pf, &l2.w_pair_sc_f16);
+        if (rc) break;
+        pack_tc_pair_fused_sc(tensors[i], co, ci, l2.sc_cin_pad, l2.cout_pad, l2.kh, l2.kw, true, pf.data());
+        rc = dev_upload(ws, pf, &l2.w_pair_sc_bf16);
+    }
     if (rc == PMP_OK) rc = build_stem_tc(ws, net, spec, tensors);
     if (rc != PMP_OK) {
         weights_destroy(h, id);
@@ -228,6 +246,7 @@ int weights_destroy(Handle *h, int wset)
 struct ConvOpts {
     int relu = 0, pool = 1;
     Act res, mul;
+    Act sc_in;                        // fuse the block's 1x1 shortcut conv on this input (instead of `res`)
     int pad_t = -1, pad_l = -1;       // -1: "same" padding k/2
     int Ho = 0, Wo = 0;               // 0: same as input
     int out_c_off = 0;
@@ -281,6 +300,11 @@ struct Net {
                             !w->bias && out.C == w->cout && in.C == w->cin && (!o.res.p || o.res.fmt == FMT_SPLIT) &&
                             (!o.mul.p || o.mul.fmt == FMT_SPLIT) && (in.bf16 ? w->w_tc_bf16 : w->w_tc_f16) &&
                             tc_supported(w->cin_pad, w->cout_pad, w->kh, w->kw, in.H, in.W);
+        if (o.sc_in.C && !use_tc) {
+            set_error("conv '%s': fused shortcut requested on a layer the TC engine does not run", name.c_str());
+            rc = PMP_ERR_STATE;
+            return;
+        }
         if (use_tc) {
             TcConvArgs a;
             a.in = in; a.res = o.res; a.mul = o.mul;
@@ -288,6 +312,10 @@ struct Net {
             a.w_pair = in.bf16 ? w->w_pair_bf16 : w->w_pair_f16;
             a.cin_pad = w->cin_pad; a.cout_pad = w->cout_pad; a.kh = w->kh; a.kw = w->kw; a.pad_t = pad_t; a.pad_l = pad_l;
             a.relu = o.relu; a.pool = 1;
+            if (o.sc_in.p || (dry && o.sc_in.C)) {
+                a.sc_in = o.sc_in; a.sc_cin_pad = w->sc_cin_pad;
+                a.w_pair_sc = in.bf16 ? w->w_pair_sc_bf16 : w->w_pair_sc_f16;
+            }
             if (o.pool == 2) {
                 // v1: un-pooled conv into a temporary, then a pooling pass (mul applies after pooling)
                 Act tmp = act(out.C, in.H, in.W);
@@ -350,9 +378,18 @@ struct Net {
         ConvOpts o2;
         o2.relu = 1; o2.pool = pool; o2.mul = mul;
         if (in.C != cout) {
-            Act sc = act(cout, in.H, in.W);
-            conv(p + ".shortcut.0", in, sc, ConvOpts());
-            o2.res = sc;
+            // the 1x1 shortcut conv: fused into the second conv as extra K groups on the TC engine (no `sc` tensor through
+            // HBM, no bandwidth-bound launch), a separate conv + residual add otherwise
+            const ConvW *w2 = weights(p + ".left.2");
+            const bool fuse = tc && tc_fusion_available() && w2 && w2->w_pair_sc_f16 && in.fmt == FMT_SPLIT && w2->sc_cin == in.C &&
+                              tc_supported(w2->cin_pad, w2->cout_pad, w2->kh, w2->kw, in.H, in.W);
+            if (fuse) {
+                o2.sc_in = in;
+            } else {
+                Act sc = act(cout, in.H, in.W);
+                conv(p + ".shortcut.0", in, sc, ConvOpts());
+                o2.res = sc;
+            }
         } else {
             o2.res = in;
         }

@@ -39,6 +39,20 @@ VARIANTS = [((64, 64, 3, 32, 5, 3), 1 << 11), ((64, 64, 3, 32, 5, 3), 1 << 10), 
             ((64, 64, 5, 32, 333, 3), 1 << 10), ((32, 64, 5, 32, 200, 1), 1 << 10), ((64, 64, 5, 64, 3, 1), 1 << 11)]
 
 
+def _fused(cin2):
+    return (1 << 17) | (cin2 << 20)
+
+
+# 1x1 shortcut conv fused into the conv as extra K groups of a second input (flag bit 17, channels in bits 20..27): every
+# ResidualBlock shape of the four nets that has a shortcut (Model_QBD.py:34-38), checked against conv + separate 1x1 conv
+VARIANTS += [((64, 64, 5, 64, 5, 1), _fused(32)), ((64, 64, 5, 64, 150, 1), _fused(32)), ((64, 64, 3, 32, 7, 1), _fused(32)),
+             ((64, 64, 5, 32, 9, 1), _fused(32)), ((32, 32, 3, 16, 9, 1), _fused(64)), ((32, 32, 3, 16, 301, 1), _fused(128)),
+             ((32, 32, 3, 16, 5, 1), _fused(3)), ((32, 32, 3, 32, 6, 1), _fused(3)), ((16, 16, 3, 32, 6, 1), _fused(32)),
+             ((16, 16, 3, 16, 7, 1), _fused(32)), ((8, 8, 3, 16, 5, 1), _fused(16)), ((8, 8, 3, 32, 5, 1), _fused(16)),
+             ((8, 8, 3, 8, 5, 1), _fused(32)), ((64, 64, 3, 16, 5, 5), _fused(32)), ((64, 64, 3, 32, 201, 5), _fused(32)),
+             ((32, 32, 3, 32, 3, 1), _fused(64))]
+
+
 @pytest.mark.parametrize("cfg,mode", VARIANTS, ids=lambda v: str(v).replace(" ", ""))
 def test_tc_conv_variants(cfg, mode):
     cin, cout, k, hw, b, fl = cfg
