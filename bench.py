@@ -249,10 +249,8 @@ def main():
         return pp.predict_frames(dy, du, dv, qps=QPS)
 
     def step_e2e():
-        res = pp.predict_frames(hy, hu, hv, qps=QPS)
-        for k, t in res.items():
-            host_out[k].copy_(t, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        pp.predict_frames(hy, hu, hv, qps=QPS, host_out=host_out)      # D2H of each component overlaps the next one
+        pp.synchronize()
 
     def barrier():
         torch.cuda.synchronize()

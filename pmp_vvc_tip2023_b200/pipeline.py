@@ -25,6 +25,7 @@ class PartitionPredictor:
         self.set_engine(engine, tc_dtype)
         self.chunk = int(chunk)
         self._wsets = {}           # (comp, qp) -> (wset_q, wset_msbd)
+        self._copy_stream = None   # device->host copies of finished components overlap the next component's kernels
 
     def set_engine(self, engine, tc_dtype="fp16"):
         eng = {"simt": _lib.ENGINE_SIMT, "tc": _lib.ENGINE_TC}[engine]
@@ -93,9 +94,12 @@ class PartitionPredictor:
         wq, wb = self._wsets[(comp, qp)]
         return ops.run_component(wq, wb, comp == "Luma", blocks, frames, bh, bw, self.chunk, want_maps)
 
-    def predict_frames(self, y, u, v, qps=(32,), comps=COMPS, want_maps=False):
+    def predict_frames(self, y, u, v, qps=(32,), comps=COMPS, want_maps=False, host_out=None):
         """y [F,H,W], u/v [F,H/2,W/2] (uint8, or uint16/int16 holding 10-bit samples), host or device.
-        Returns {(comp, qp): int8 CUDA tensor [F, per-frame values]} (or tuples with maps)."""
+        Returns {(comp, qp): int8 CUDA tensor [F, per-frame values]} (or tuples with maps).
+
+        host_out: optional {(comp, qp): pinned int8 host tensor [F, per-frame values]}; each finished component is then
+        copied to the host on a side stream while the next one computes -- call ``synchronize()`` before reading them."""
         f, hgt, wid = y.shape
         bh, bw = hgt // 64, wid // 64
         lb, cb = self.cut(y, u, v, comps)
@@ -103,8 +107,25 @@ class PartitionPredictor:
         for comp in comps:
             blocks = lb if comp == "Luma" else cb
             for qp in qps:
-                out[(comp, qp)] = self.predict_blocks(comp, qp, blocks, f, bh, bw, want_maps)
+                res = self.predict_blocks(comp, qp, blocks, f, bh, bw, want_maps)
+                out[(comp, qp)] = res
+                if host_out is not None:
+                    vec = res[0] if want_maps else res
+                    if self._copy_stream is None:
+                        self._copy_stream = torch.cuda.Stream(self.device)
+                    done = torch.cuda.Event()
+                    done.record(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(self._copy_stream):
+                        self._copy_stream.wait_event(done)
+                        host_out[(comp, qp)].copy_(vec, non_blocking=True)
+                    vec.record_stream(self._copy_stream)
         return out
+
+    def synchronize(self):
+        """Wait for the compute stream and for the host copies queued by ``predict_frames(host_out=...)``."""
+        torch.cuda.current_stream(self.device).synchronize()
+        if self._copy_stream is not None:
+            self._copy_stream.synchronize()
 
     @staticmethod
     def partition_path(save_dir, seq_path_name, comp, qp):
