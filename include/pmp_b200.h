@@ -137,7 +137,8 @@ int pmp_run_component(pmp_handle *h, int wset_q, int wset_msbd, int luma, const 
  * bit10 CTA-pair (cta_group::2) kernel, bit11 force the single-CTA kernel, bit12 unstacked accumulators for the
  * 3x3 Cout = 64 layers (A/B of the default stacked scheme), bits 13..15 cap on the number of whole-tile
  * activation buffers (0: default); bit16 verbose mismatch report on stderr; bit17 fused 1x1 shortcut conv on a second
- * input with ((flags >> 20) & 0xff, default 32) channels (checked against conv + separate 1x1 conv; excludes bit1). */
+ * input with ((flags >> 20) & 0xff, default 32) channels (checked against conv + separate 1x1 conv; excludes bit1); bit18 2x2 max-pool with the horizontal half
+ * fused into the conv epilogue (checked against the exact conv with fused pooling; excludes bit2). */
 int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, int hw, int batch, int flags,
                       double *max_err, double *ref_absmax, double *ms_tc, double *ms_simt);
 

@@ -344,7 +344,7 @@ struct TcParams {
     Act out, res, mul;
     int H, W, P, kh, kw, pady, padx, groups, total_mt, tiles, N1, coutp, nstages, items;
     uint32_t plane_bytes, group_bytes, stage_bytes, tmem_cols, idesc1, idesc2;
-    int relu, stacked, pairbuf, nbuf, dbg;
+    int relu, stacked, pairbuf, nbuf, dbg, hpool;
     int nslot, mt_alloc, acc_cols;      // CTA-pair kernel: accumulator slot ring (slots, M-tiles per tile, columns per slot)
     int aslots, groups2;                // CTA-pair kernel: activation slot ring (one channel-group box each); fused shortcut groups
     int B, pair_items;      // CTA-pair kernel: images in the batch, work items = tiles * ceil(B/2)
@@ -448,6 +448,46 @@ __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t tadd
 #pragma unroll
             for (int e = 0; e < 8; e++) v[j][e] = __uint_as_float(a[e]);
         }
+    }
+    if (p.hpool) {
+        // Horizontal half of a fused 2x2 max-pool (pooled ResidualBlocks have no bias / attention product here and an
+        // identity-or-fused shortcut): the pair (c, c+1), c even, sits in adjacent lanes (the pitch is even), so the
+        // exchange is one shuffle per value -- every lane takes part, also the ones on pad columns.  relu(max) == max(relu),
+        // but the residual must be added before the max: done here, ahead of the common path.
+        if (p.res.p) {
+            const bool bfr = p.out.bf16 != 0;
+#pragma unroll
+            for (int j = 0; j < CH; j++) {
+                float rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (valid) unpack_split(rh[j], rl[j], bfr, rv);
+#pragma unroll
+                for (int e = 0; e < 8; e++) v[j][e] += rv[e];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CH; j++)
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[j][e] = fmaxf(v[j][e], __shfl_xor_sync(0xffffffffu, v[j][e], 1));
+        if (!valid || (c & 1)) return;
+        const bool bfh = p.out.bf16 != 0;
+        const size_t hplane = (size_t)p.H * (p.W >> 1);
+        uint4 *obh = reinterpret_cast<uint4 *>(p.out.p) + (size_t)n * (p.out.Cp >> 2) * hplane + (size_t)r * (p.W >> 1) + (c >> 1);
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            if (p.relu) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) v[j][e] = fmaxf(v[j][e], 0.f);
+            }
+            uint4 Hh, Ll;
+            split2(v[j][0], v[j][1], bfh, Hh.x, Ll.x);
+            split2(v[j][2], v[j][3], bfh, Hh.y, Ll.y);
+            split2(v[j][4], v[j][5], bfh, Hh.z, Ll.z);
+            split2(v[j][6], v[j][7], bfh, Hh.w, Ll.w);
+            uint4 *q = obh + (size_t)split_plane(ch0 + j, 0) * hplane;
+            q[0] = Hh;
+            q[2 * hplane] = Ll;
+        }
+        return;
     }
     if (!valid) return;
     const bool bf = p.out.bf16 != 0;
@@ -1113,7 +1153,8 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     const bool use_pair = geom_ok;
     if (!geom_ok) geom_ok = tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g);
     if (a.in.fmt != FMT_SPLIT || a.out.fmt != FMT_SPLIT || !geom_ok ||
-        a.in.Cp != a.cin_pad || a.out.Cp != a.cout_pad || a.pool != 1 || a.out.H != H || a.out.W != W) {
+        a.in.Cp != a.cin_pad || a.out.Cp != a.cout_pad || a.pool != 1 || a.out.H != H || a.out.W != (a.hpool ? W / 2 : W) ||
+        (a.hpool && (!use_pair || a.bias || a.mul.p))) {
         set_error("conv_tc: unsupported configuration cin %d cout %d k %dx%d %dx%d", a.cin_pad, a.cout_pad, a.kh, a.kw, H, W);
         return PMP_ERR_UNSUPPORTED;
     }
@@ -1147,7 +1188,7 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     const uint32_t idesc_base = idesc_base_nom | ((128u >> 4) << 24);
     p.idesc1 = idesc_base | ((uint32_t)(g.N1 >> 3) << 17);
     p.idesc2 = idesc_base | ((uint32_t)(g.coutp >> 3) << 17);
-    p.relu = a.relu; p.stacked = g.stacked; p.pairbuf = g.pairbuf; p.nbuf = g.nbuf;
+    p.relu = a.relu; p.stacked = g.stacked; p.pairbuf = g.pairbuf; p.nbuf = g.nbuf; p.hpool = a.hpool;
     static const int env_dbg = [] { const char *e = getenv("PMP_TC_DBG"); return e ? atoi(e) : 0; }();   // timing experiments only
     p.dbg = env_dbg;
     if (!h->tc_attr_set) {          // function attributes are per device: one handle per device
@@ -1261,7 +1302,8 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------
 // max-pool 2x2 (+ attention product) on split tensors; format conversion helpers
 // ------------------------------------------------------------------------------------------------
-__global__ void pool2_split_kernel(Act in, Act out, Act mul, int B)
+// hdone: the producing conv's epilogue already took the horizontal maximum (`in` is H x W/2): vertical half only
+__global__ void pool2_split_kernel(Act in, Act out, Act mul, int B, int hdone)
 {
     const int Ho = out.H, Wo = out.W, nch = out.Cp >> 3;
     size_t total = (size_t)B * nch * Ho * Wo;
@@ -1269,6 +1311,19 @@ __global__ void pool2_split_kernel(Act in, Act out, Act mul, int B)
         int x = (int)(i % Wo), y = (int)((i / Wo) % Ho), ch = (int)((i / ((size_t)Wo * Ho)) % nch);
         int n = (int)(i / ((size_t)Wo * Ho * nch));
         float m[8], v[8];
+        if (hdone) {
+            load_chunk_split(in, n, ch, 2 * y, x, m);
+            load_chunk_split(in, n, ch, 2 * y + 1, x, v);
+#pragma unroll
+            for (int e = 0; e < 8; e++) m[e] = fmaxf(m[e], v[e]);
+            if (mul.p) {
+                load_chunk_split(mul, n, ch, y, x, v);
+#pragma unroll
+                for (int e = 0; e < 8; e++) m[e] *= v[e];
+            }
+            store_chunk_split(out, n, ch, y, x, m);
+            continue;
+        }
         load_chunk_split(in, n, ch, 2 * y, 2 * x, m);
         load_chunk_split(in, n, ch, 2 * y, 2 * x + 1, v);
 #pragma unroll
@@ -1292,9 +1347,10 @@ int pool2_split(Handle *h, const Act &in, const Act &out, const Act &mul, int B,
 {
     size_t total = (size_t)B * (out.Cp >> 3) * out.H * out.W;
     if (!total) return PMP_OK;
+    const int hdone = in.W == out.W ? 1 : 0;
     int grid = (int)((total + 255) / 256);
-    ProfScope ps(h, PROF_ELEMWISE, s, 0, (double)total * 32 * 5);
-    pool2_split_kernel<<<grid, 256, 0, s>>>(in, out, mul, B);
+    ProfScope ps(h, PROF_ELEMWISE, s, 0, (double)total * 32 * (hdone ? 3 : 5));
+    pool2_split_kernel<<<grid, 256, 0, s>>>(in, out, mul, B, hdone);
     h->launches++;
     PMP_CUDA(cudaGetLastError());
     return PMP_OK;
@@ -1510,6 +1566,13 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     if (flags & 4) sa.mul = mul;
     sa.w = (const float *)d_wsimt.p; sa.cin = cin; sa.cout = cout; sa.coutw = coutw;
     sa.pad_t = sa.pad_l = ksize / 2; sa.Ho = H; sa.Wo = W; sa.relu = flags & 1; sa.pool = 1;
+    // bit 18: 2x2 max-pool -- horizontal half in the conv epilogue, vertical half by pool2_split -- against the exact conv
+    // with its fused 2x2 pooling (excludes the attention product)
+    const bool pooled = (flags >> 18) & 1;
+    if (pooled) {
+        if ((flags & 4) || (W & 1) || (H & 1)) { set_error("selftest: pooled variant needs even sizes and no attention product"); return PMP_ERR_ARG; }
+        sa.pool = 2; sa.out.H = H / 2; sa.out.W = W / 2;
+    }
     int rc = PMP_OK;
     if (fused) {            // reference: exact fp32 1x1 conv of the second input, added as the residual of the main conv
         SimtConvArgs sc;
@@ -1529,6 +1592,7 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     ta.in = in; ta.out = out;
     if (flags & 2) ta.res = res;
     if (flags & 4) ta.mul = mul;
+    if (pooled) { ta.hpool = 1; ta.out.W = W / 2; out.W = W / 2; }
     ta.w = (const uint16_t *)d_wtc.p; ta.w_pair = (const uint16_t *)d_wpair.p; ta.cin_pad = cinp; ta.cout_pad = coutp; ta.kh = ta.kw = ksize; ta.pad_t = ta.pad_l = ksize / 2; ta.relu = flags & 1; ta.pool = 1;
     if (fused) { ta.sc_in = in2; ta.w_pair_sc = (const uint16_t *)d_wsc.p; ta.sc_cin_pad = cin2p; }
     pmp::g_tc_scheme = ((flags >> 8) & 3) - 1;          // 0: library default, 1: unstacked, 2: stacked
@@ -1540,6 +1604,13 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     if (!rc) rc = conv_tc(h, ta, B, s);
     cudaEventRecord(e3, s);
     if (rc) return rc;
+    if (pooled) {           // `out` holds H x W/2 (d_out is large enough); finish the pool into the d_res buffer (free by now)
+        Act pooled_out = mk(d_res.p, cout);
+        pooled_out.H = H / 2; pooled_out.W = W / 2;
+        rc = pool2_split(h, out, pooled_out, Act(), B, s);
+        if (rc) return rc;
+        out = pooled_out;
+    }
     split_to_f32_kernel<<<1024, 256, 0, s>>>(out, (float *)d_out32.p, B);
     cudaError_t ce = cudaStreamSynchronize(s);
     if (ce != cudaSuccess) return cuda_fail(ce, "selftest sync", __FILE__, __LINE__);
@@ -1547,12 +1618,14 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     cudaEventElapsedTime(&t_simt, e0, e1);
     cudaEventElapsedTime(&t_tc, e2, e3);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
-    std::vector<float> got(n_out), want(n_out);
-    PMP_CUDA(cudaMemcpy(got.data(), d_out32.p, n_out * 4, cudaMemcpyDeviceToHost));
-    PMP_CUDA(cudaMemcpy(want.data(), d_ref32.p, n_out * 4, cudaMemcpyDeviceToHost));
+    const size_t n_full = n_out;
+    const size_t n_cmp = pooled ? n_full / 4 : n_full;
+    std::vector<float> got(n_cmp), want(n_cmp);
+    PMP_CUDA(cudaMemcpy(got.data(), d_out32.p, n_cmp * 4, cudaMemcpyDeviceToHost));
+    PMP_CUDA(cudaMemcpy(want.data(), d_ref32.p, n_cmp * 4, cudaMemcpyDeviceToHost));
     double me = 0, am = 0;
     size_t nbad = 0, first_bad = (size_t)-1;
-    for (size_t i = 0; i < n_out; i++) {
+    for (size_t i = 0; i < n_cmp; i++) {
         double e = fabs((double)got[i] - (double)want[i]);
         if (!(e == e)) e = 1e30;
         if (e > me) me = e;
@@ -1561,10 +1634,10 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     }
     if ((flags & (1 << 16)) && nbad) {
         fprintf(stderr, "[selftest] cin %d cout %d k %d hw %d B %d flags %x: %zu/%zu bad, max err %g (ref absmax %g)\n", cin,
-                cout, ksize, hw, B, flags, nbad, n_out, me, am);
+                cout, ksize, hw, B, flags, nbad, n_cmp, me, am);
         // error map by (y, x) for image 0 / channel 0 and by channel at pixel (H/2, W/2)
         int shown = 0;
-        for (size_t i = first_bad; i < n_out && shown < 12; i++) {
+        for (size_t i = first_bad; i < n_cmp && shown < 12; i++) {
             double e = fabs((double)got[i] - (double)want[i]);
             if (e > 1e-3 * (1.0 + fabs(want[i])) || !(e == e)) {
                 int x = (int)(i % W), y = (int)((i / W) % H), c = (int)((i / ((size_t)W * H)) % cout), n = (int)(i / ((size_t)W * H * cout));
@@ -1573,7 +1646,7 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
             }
         }
         std::vector<int> by_y(H, 0), by_x(W, 0), by_c(cout, 0);
-        for (size_t i = 0; i < n_out; i++) {
+        for (size_t i = 0; i < n_cmp; i++) {
             double e = fabs((double)got[i] - (double)want[i]);
             if (e > 1e-3 * (1.0 + fabs(want[i])) || !(e == e)) {
                 by_x[i % W]++; by_y[(i / W) % H]++; by_c[(i / ((size_t)W * H)) % cout]++;

@@ -43,6 +43,8 @@ struct TcConvArgs {
     int pad_t = 0, pad_l = 0;       // input coordinate = output coordinate + tap - pad
     int Ho = 0;                     // output rows (0: same as the input)
     int relu = 0, pool = 1;
+    int hpool = 0;                  // epilogue takes the horizontal maximum of pixel pairs: `out` is H x W/2 (CTA-pair kernel;
+                                    // pool2_split then finishes the 2x2 max-pool with the vertical half)
     double flops_override = 0;      // algorithmic FLOPs per image for the profile (0: from the shapes)
 };
 int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s);

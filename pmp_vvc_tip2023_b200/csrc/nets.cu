@@ -317,9 +317,12 @@ struct Net {
                 a.w_pair_sc = in.bf16 ? w->w_pair_sc_bf16 : w->w_pair_sc_f16;
             }
             if (o.pool == 2) {
-                // v1: un-pooled conv into a temporary, then a pooling pass (mul applies after pooling)
-                Act tmp = act(out.C, in.H, in.W);
-                a.out = tmp; a.mul = Act();
+                // the conv's epilogue takes the horizontal maximum (half-width temporary), a pooling pass the vertical
+                // one (mul applies after pooling); without the CTA-pair kernel: un-pooled temporary + full 2x2 pass
+                static const int env_hp = [] { const char *e = getenv("PMP_TC_HPOOL"); return e ? atoi(e) : 1; }();   // A/B knob
+                const bool hp = env_hp && tc_fusion_available() && !(in.W & 1);
+                Act tmp = act(out.C, in.H, hp ? in.W / 2 : in.W);
+                a.out = tmp; a.mul = Act(); a.hpool = hp ? 1 : 0;
                 if (!dry) {
                     rc = conv_tc(h, a, B, s);
                     if (!rc) rc = pool2_split(h, tmp, out, o.mul, B, s);

@@ -61,3 +61,15 @@ def test_tc_conv_variants(cfg, mode):
     _lib.check(_lib.lib().pmp_selftest_conv(h.ptr, cin, cout, k, hw, b, fl | mode, ctypes.byref(me), ctypes.byref(am),
                                             ctypes.byref(t1), ctypes.byref(t2)))
     assert me.value <= 2e-5 * max(am.value, 1.0), (me.value, am.value)
+
+
+# 2x2 max-pool: horizontal half in the conv epilogue (flag bit 18), vertical half by pool2_split; the pooled ResidualBlock
+# shapes of the nets (identity residual or fused shortcut)
+POOLED = [((64, 64, 5, 64, 5, 1), (1 << 18) | _fused(32)), ((64, 64, 3, 64, 75, 3), 1 << 18), ((64, 64, 5, 32, 9, 3), 1 << 18),
+          ((64, 64, 3, 32, 201, 3), 1 << 18), ((32, 32, 3, 16, 7, 3), 1 << 18), ((8, 8, 3, 32, 5, 1), (1 << 18) | _fused(16)),
+          ((64, 64, 3, 32, 4, 1), 1 << 18)]
+
+
+@pytest.mark.parametrize("cfg,mode", POOLED, ids=lambda v: str(v).replace(" ", ""))
+def test_tc_conv_fused_hpool(cfg, mode):
+    test_tc_conv_variants(cfg, mode)
