@@ -58,8 +58,15 @@ class _PmpNet(nn.Module):
         return st
 
     def _param_list(self):
-        sd = dict(self.named_parameters())
-        return [sd[name] for name, _ in param_spec(self.NET)]
+        # attribute walk, not named_parameters(): nn.DataParallel replicas on the other GPUs carry their weights as plain
+        # tensor attributes (torch/nn/parallel/replicate.py), their _parameters dicts are empty
+        out = []
+        for name, _ in param_spec(self.NET):
+            obj = self
+            for part in name.split("."):
+                obj = getattr(obj, part)
+            out.append(obj)
+        return out
 
     def _weight_set(self, device):
         params = self._param_list()
