@@ -8,6 +8,7 @@
 // This kernel is (a) the whole conv path of PMP_ENGINE_SIMT (fp32 NCHW everywhere) and (b) inside
 // PMP_ENGINE_TC the path of the layers that do not fit tensor cores: the stems (Cin <= 4, u8/f32 in,
 // split out), the 8x8 tail of the Q nets and the Cout <= 2 output convs (split in, fp32 out).
+#include <cstdlib>
 #include "handle.cuh"
 #include "tensor.cuh"
 #include "kernels.cuh"
@@ -172,9 +173,61 @@ static int launch_simt(Handle *h, const SimtConvArgs &a, int B, cudaStream_t s)
     return PMP_OK;
 }
 
+// The output convs of the TC engine's nets (conv_q2, conv_B1..3: 3x3 "same", 8 -> 1 or 2 channels on a 8x8 / 16x16 map, bias,
+// optional running sum into channel 0, fp32 outputs): the general kernel above would spend 15/16 of its lanes on channels
+// that do not exist.  One CTA per image, one thread per output pixel, the 8-channel input chunk staged in shared memory.
+// Same accumulation order as conv_simt_kernel (ci, ky, kx; bias and add0 afterwards): bit-identical results.
+__global__ void __launch_bounds__(256)
+outconv3x3_kernel(SimtConvArgs a)
+{
+    __shared__ float s_in[8][18][19];
+    __shared__ float s_w[8 * 9 * 2];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const int H = a.in.H, W = a.in.W;
+    for (int k = tid; k < (H + 2) * (W + 2); k += 256) {
+        const int r = k / (W + 2), c = k - r * (W + 2), iy = r - 1, ix = c - 1;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) load_chunk_split(a.in, n, 0, iy, ix, v);
+#pragma unroll
+        for (int ci = 0; ci < 8; ci++) s_in[ci][r][c] = v[ci];
+    }
+    for (int k = tid; k < 8 * 9 * 2; k += 256) {
+        const int co = k & 1, t = (k >> 1) % 9, ci = k / 18;
+        s_w[k] = (ci < a.cin && co < a.cout) ? a.w[((size_t)ci * 9 + t) * a.coutw + co] : 0.f;
+    }
+    __syncthreads();
+    if (tid >= H * W) return;
+    const int oy = tid / W, ox = tid - oy * W;
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 1
+    for (int ci = 0; ci < a.cin; ci++)
+#pragma unroll
+        for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+                const float v = s_in[ci][oy + ky][ox + kx];
+                acc0 = fmaf(v, s_w[(ci * 9 + ky * 3 + kx) * 2], acc0);
+                acc1 = fmaf(v, s_w[(ci * 9 + ky * 3 + kx) * 2 + 1], acc1);
+            }
+    if (a.bias) { acc0 += a.bias[0]; if (a.cout > 1) acc1 += a.bias[1]; }
+    if (a.add0) acc0 += a.add0[(size_t)n * a.add0_bstride + (size_t)oy * a.Wo + ox];
+    store_elem_f32(a.out, n, 0, oy, ox, acc0);
+    if (a.cout > 1) store_elem_f32(a.out, n, 1, oy, ox, acc1);
+}
+
 int conv_simt(Handle *h, const SimtConvArgs &a, int kh, int kw, int B, cudaStream_t s)
 {
     if (B <= 0) return PMP_OK;
+    static const int env_oc = [] { const char *e = getenv("PMP_OUTCONV"); return e ? atoi(e) : 1; }();      // A/B knob
+    if (env_oc && kh == 3 && kw == 3 && a.cout <= 2 && a.cin <= 8 && a.in.fmt == FMT_SPLIT && a.in.H <= 16 && a.in.W <= 16 &&
+        a.Ho == a.in.H && a.Wo == a.in.W && a.pad_t == 1 && a.pad_l == 1 && !a.res.p && !a.mul.p && !a.relu && a.pool == 1 &&
+        a.out_c_off == 0 && (a.out.fmt == FMT_F32 || a.out.fmt == FMT_PAIR)) {
+        ProfScope ps(h, PROF_CONV_SIMT, s, 2.0 * B * a.Ho * a.Wo * a.cout * a.cin * 9, 0);
+        outconv3x3_kernel<<<B, 256, 0, s>>>(a);
+        h->launches++;
+        PMP_CUDA(cudaGetLastError());
+        return PMP_OK;
+    }
 #define PMP_K(H_, W_, C_) if (kh == H_ && kw == W_) return launch_simt<H_, W_, C_>(h, a, B, s)
     PMP_K(1, 1, 8); PMP_K(3, 3, 8); PMP_K(5, 5, 8); PMP_K(9, 9, 2); PMP_K(5, 9, 2); PMP_K(9, 5, 2); PMP_K(3, 5, 4);
     PMP_K(5, 3, 4);

@@ -423,8 +423,12 @@ __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t tadd
     const size_t pix = (size_t)r * p.W + c;
     uint4 rh[CH], rl[CH];
     // residual operand first: its latency overlaps the TMEM loads
-    if (p.res.p && valid) {
-        const uint4 *rb = reinterpret_cast<const uint4 *>(p.res.p) + (size_t)n * (p.res.Cp >> 2) * plane + pix;
+    // (the attention product's operand takes the residual's registers when there is no residual -- the Att trunks' last
+    // block has a fused shortcut -- so that its latency overlaps the TMEM loads too)
+    const bool mul_early = p.mul.p && !p.res.p;
+    if ((p.res.p || mul_early) && valid) {
+        const Act &t = p.res.p ? p.res : p.mul;
+        const uint4 *rb = reinterpret_cast<const uint4 *>(t.p) + (size_t)n * (t.Cp >> 2) * plane + pix;
 #pragma unroll
         for (int j = 0; j < CH; j++) {
             const uint4 *q = rb + (size_t)split_plane(ch0 + j, 0) * plane;
@@ -510,11 +514,15 @@ __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t tadd
 #pragma unroll
             for (int e = 0; e < 8; e++) v[j][e] = fmaxf(v[j][e], 0.f);
         }
-        if (p.mul.p) {      // attention product: only the last conv of the two Att trunks, latency not hidden
-            const uint4 *q = reinterpret_cast<const uint4 *>(p.mul.p) + (size_t)n * (p.mul.Cp >> 2) * plane + pix +
-                             (size_t)split_plane(ch0 + j, 0) * plane;
+        if (p.mul.p) {      // attention product: only the last conv of the two Att trunks
             float mv[8];
-            unpack_split(ldg_stream(q), ldg_stream(q + 2 * plane), bf, mv);
+            if (mul_early) {
+                unpack_split(rh[j], rl[j], bf, mv);
+            } else {
+                const uint4 *q = reinterpret_cast<const uint4 *>(p.mul.p) + (size_t)n * (p.mul.Cp >> 2) * plane + pix +
+                                 (size_t)split_plane(ch0 + j, 0) * plane;
+                unpack_split(ldg_stream(q), ldg_stream(q + 2 * plane), bf, mv);
+            }
 #pragma unroll
             for (int e = 0; e < 8; e++) v[j][e] *= mv[e];
         }

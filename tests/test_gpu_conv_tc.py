@@ -65,6 +65,10 @@ def test_tc_conv_variants(cfg, mode):
 
 # 2x2 max-pool: horizontal half in the conv epilogue (flag bit 18), vertical half by pool2_split; the pooled ResidualBlock
 # shapes of the nets (identity residual or fused shortcut)
+# a batch of one runs the pair kernel too (the peer CTA recomputes the image and drops it)
+VARIANTS += [((64, 64, 3, 32, 1, 3), 0), ((32, 32, 3, 16, 1, 1), _fused(64)), ((64, 64, 5, 64, 1, 3), 1 << 18),
+             ((64, 32, 3, 16, 1, 1), 0)]
+
 POOLED = [((64, 64, 5, 64, 5, 1), (1 << 18) | _fused(32)), ((64, 64, 3, 64, 75, 3), 1 << 18), ((64, 64, 5, 32, 9, 3), 1 << 18),
           ((64, 64, 3, 32, 201, 3), 1 << 18), ((32, 32, 3, 16, 7, 3), 1 << 18), ((8, 8, 3, 32, 5, 1), (1 << 18) | _fused(16)),
           ((64, 64, 3, 32, 4, 1), 1 << 18)]

@@ -10,7 +10,7 @@ import bench  # noqa: E402
 
 def main():
     frames = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-    pp = bench.load_predictor(0, "tc", 480)
+    pp = bench.load_predictor(0, "tc", int(sys.argv[2]) if len(sys.argv) > 2 else 480)
     y, u, v = bench.make_frames(100)
     for _ in range(2):
         pp.predict_frames(y[:frames], u[:frames], v[:frames], qps=(32,))
