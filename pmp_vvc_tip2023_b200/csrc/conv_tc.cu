@@ -95,7 +95,8 @@ static void tc_ring_layout(TcGeom &g, uint32_t slab, int taps)
     g.smem_bytes = TC_SMEM_HEADER + (uint32_t)nb * g.act_bytes + (uint32_t)g.nstages * slab;
 }
 
-static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W, TcGeom &g, int scheme_override = -1, bool pair = false)
+static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W, TcGeom &g, int scheme_override = -1, bool pair = false,
+                        int ppg = 4)        // planes per channel group in shared memory: hi + lo k8 halves, or hi only (stems)
 {
     if (kh < 1 || kh > 9 || kw < 1 || kw > 5) return false;
     if (cin_pad % 16 || cout_pad % 16 || cin_pad < 16 || cout_pad < 16 || cout_pad > 64) return false;
@@ -124,9 +125,9 @@ static bool tc_geometry(int cin_pad, int cout_pad, int kh, int kw, int H, int W,
         int rbox = maxidx / g.P + 1;
         if (rbox > 256) continue;
         uint32_t plane = (uint32_t)rbox * g.P * 16;
-        uint32_t act = plane * 4 * g.groups;
+        uint32_t act = plane * (uint32_t)ppg * g.groups;
         if (TC_SMEM_HEADER + act + (uint32_t)(kw + 3) * g.stage_bytes > TC_SMEM_MAX) continue;  // ring >= one filter row + 2
-        g.MT = mt; g.Rbox = rbox; g.plane_bytes = plane; g.group_bytes = plane * 4; g.act_bytes = act;
+        g.MT = mt; g.Rbox = rbox; g.plane_bytes = plane; g.group_bytes = plane * (uint32_t)ppg; g.act_bytes = act;
         tc_ring_layout(g, g.stage_bytes, kh * kw);
         g.tiles = (g.total_mt + mt - 1) / mt;
         uint32_t cols = (g.stacked && !g.pairbuf ? 16u : 8u) * g.coutp, pc = 32;
@@ -347,6 +348,10 @@ struct TcParams {
     int relu, stacked, pairbuf, nbuf, dbg, hpool;
     int nslot, mt_alloc, acc_cols;      // CTA-pair kernel: accumulator slot ring (slots, M-tiles per tile, columns per slot)
     int aslots, groups2;                // CTA-pair kernel: activation slot ring (one channel-group box each); fused shortcut groups
+    // CTA-pair kernel, first-layer ("stem") mode: the A operand is assembled by TMA from 8 pre-shifted copies of each source
+    // plane (stem_shift_kernel); a K chunk of 8 unrolled channels = (plane, 8 consecutive kx shifts).  hi planes only.
+    int stem, stem_planes;
+    signed char stem_chunk_plane[8], stem_chunk_u0[8];
     int B, pair_items;      // CTA-pair kernel: images in the batch, work items = tiles * ceil(B/2)
     uint32_t pair_slab;     // CTA-pair kernel: bytes of one per-CTA weight slab
     int pair_split;         // CTA-pair kernel: rows of the weight tensor map per slab (1, or 2 for 3 KB slabs)
@@ -800,6 +805,13 @@ __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap *tmap, uint32_t leader_bar, int c0, int c1,
+                                                 int c2, int c3, int c4)
+{
+    asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *tmap, uint32_t leader_bar, int c0, int c1)
 {
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -866,6 +878,7 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
     const uint32_t peer_wempty = mapa_cluster(b.wempty, 1), peer_aempty = mapa_cluster(b.aempty, 1), peer_acc = mapa_cluster(b.acc, 1);
     const int KH = p.kh, P = p.P, NS = p.nstages, G = p.groups;
     long long st_a = 0, st_b = 0, st_c = 0;
+    const bool hi_only = p.stem != 0;            // stems: 8-bit pixels (and the pre-split qt planes) are exact in 16 bits
     const int G2 = p.groups2;                    // fused 1x1 shortcut: extra channel groups of a second input, centre tap only
     const uint32_t ASLOTS = (uint32_t)p.aslots, ctr16 = (uint32_t)(p.pady * p.P + p.padx);
     uint32_t s = 0, ph = 0, idx = 0, as = 0, aph = 0;   // weight stage / activation slot of the ring and their parities
@@ -895,7 +908,7 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
                             const uint64_t ad = ad0 + (uint64_t)j, bd = bd0 + (uint64_t)((uint32_t)j * slab16);
                             if (ST) {
                                 umma_f16_pair(d_tmem, ad, bd, idesc_st, j == 0 ? acc : 1u);     // a_hi * [w_hi | w_lo]
-                                umma_f16_pair(d_tmem, ad + lo16, bd + wlo16, idesc, 1u);        // a_lo * w_hi
+                                if (!hi_only) umma_f16_pair(d_tmem, ad + lo16, bd + wlo16, idesc, 1u);   // a_lo * w_hi
                             } else {
                                 umma_f16_pair(d_tmem, ad, bd, idesc, j == 0 ? acc : 1u);        // a_hi * w_hi
                                 umma_f16_pair(d_tmem, ad, bd + wlo16, idesc, 1u);               // a_hi * w_lo
@@ -1043,6 +1056,14 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 for (int v = 0; v < V; v++) {
                     { TC_PROF_BEGIN(prof); mbar_wait_relaxed(b.aempty + 8 * as, aph ^ 1u); TC_PROF_END(prof, st); }
                     if (rank == 0) mbar_expect_tx(b.afull + 8 * as, 2u * p.group_bytes);
+                    if (p.stem) {           // two K chunks = two boxes of 8-pixel windows: position x = 8u + s
+                        for (int kc = 0; kc < 2; kc++)
+                            tma_load_5d_pair(smem_u32(act + (size_t)as * p.group_bytes + (size_t)kc * p.plane_bytes), &tmap,
+                                             lead_afull + 8 * as, 0, 0, p.stem_chunk_u0[2 * v + kc], t.row0 - p.pady,
+                                             t.n * p.stem_planes + p.stem_chunk_plane[2 * v + kc]);
+                        if (++as == (uint32_t)p.aslots) { as = 0; aph ^= 1u; }
+                        continue;
+                    }
                     const bool second = v >= p.groups;
                     tma_load_4d_pair(smem_u32(act + (size_t)as * p.group_bytes), second ? &tmap2 : &tmap, lead_afull + 8 * as,
                                      -2 * p.padx, t.row0 - p.pady, (second ? v - p.groups : v) * 4, t.n);
@@ -1156,10 +1177,16 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     // (a batch of one runs the pair kernel too: the peer CTA recomputes the image and drops it -- one arithmetic for
     // every batch composition; the single-CTA kernel remains as the PMP_TC_PAIR=0 / self-test A-B path)
     const bool want_pair = tc_pair_default() && a.w_pair;
-    bool geom_ok = want_pair && tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g, -1, true) &&
+    const bool stem = a.stem_src != nullptr;
+    if (stem && (!want_pair || a.kw != 1 || (W & 7) || a.stem_nchunk < 1 || a.stem_nchunk > 8 || a.cin_pad != 16 * ((a.stem_nchunk + 1) / 2) ||
+                 a.sc_in.p || a.res.p || a.mul.p || a.hpool)) {
+        set_error("conv_tc: stem mode needs the CTA-pair kernel, a kh x 1 kernel, W %% 8 == 0 and 1..8 K chunks");
+        return PMP_ERR_UNSUPPORTED;
+    }
+    bool geom_ok = want_pair && tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g, -1, true, stem ? 2 : 4) &&
                    (g.stacked != 0) == tc_pair_stacked_layout(a.cout_pad, a.kh, a.kw);
     const bool use_pair = geom_ok;
-    if (!geom_ok) geom_ok = tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g);
+    if (!geom_ok && !stem) geom_ok = tc_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw, H, W, g);
     if (a.in.fmt != FMT_SPLIT || a.out.fmt != FMT_SPLIT || !geom_ok ||
         a.in.Cp != a.cin_pad || a.out.Cp != a.cout_pad || a.pool != 1 || a.out.H != H || a.out.W != (a.hpool ? W / 2 : W) ||
         (a.hpool && (!use_pair || a.bias || a.mul.p))) {
@@ -1178,8 +1205,22 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)Hin * W * 16, planes * Hin * W * 16};
     cuuint32_t box[4] = {(cuuint32_t)g.P * 2, (cuuint32_t)g.Rbox, 4, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, a.in.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult cr;
+    if (stem) {
+        // 8 pre-shifted copies per source plane, [B * planes][rows][uw][shift s][8 pixels] 16-bit: the unit (y, u, s) holds
+        // pixels 8u+s .. 8u+s+7 of row y.  A box (16 B, 8 shifts, W/8 units, Rbox rows) lands them as positions x = 8u + s,
+        // each with its 8-pixel window = 8 consecutive kx shifts: the unrolled K chunk, assembled by the TMA engine.
+        cuuint64_t sdim[5] = {2, 8, (cuuint64_t)a.stem_uw, (cuuint64_t)a.stem_rows, (cuuint64_t)B * a.stem_planes};
+        cuuint64_t sstr[4] = {16, 128, (cuuint64_t)a.stem_uw * 128, (cuuint64_t)a.stem_rows * a.stem_uw * 128};
+        cuuint32_t sbox[5] = {2, 8, (cuuint32_t)W / 8, (cuuint32_t)g.Rbox, 1};
+        cuuint32_t sest[5] = {1, 1, 1, 1, 1};
+        cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void *>(a.stem_src), sdim, sstr, sbox, sest,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, a.in.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (cr != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) for W %d H %d planes %d B %d box %d x %d", (int)cr, W, H, (int)planes, B,
                   g.P, g.Rbox);
@@ -1197,6 +1238,12 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     p.idesc1 = idesc_base | ((uint32_t)(g.N1 >> 3) << 17);
     p.idesc2 = idesc_base | ((uint32_t)(g.coutp >> 3) << 17);
     p.relu = a.relu; p.stacked = g.stacked; p.pairbuf = g.pairbuf; p.nbuf = g.nbuf; p.hpool = a.hpool;
+    p.stem = stem ? 1 : 0; p.stem_planes = a.stem_planes;
+    for (int c = 0; c < 8; c++) {           // an odd chunk count repeats chunk 0 (its weights are zero; the operand must be finite)
+        const int src = c < a.stem_nchunk ? c : 0;
+        p.stem_chunk_plane[c] = stem ? a.stem_chunk_plane[src] : 0;
+        p.stem_chunk_u0[c] = stem ? a.stem_chunk_u0[src] : 0;
+    }
     static const int env_dbg = [] { const char *e = getenv("PMP_TC_DBG"); return e ? atoi(e) : 0; }();   // timing experiments only
     p.dbg = env_dbg;
     if (!h->tc_attr_set) {          // function attributes are per device: one handle per device
@@ -1395,6 +1442,54 @@ int stem_unroll(Handle *h, const Act &x, const float *qt, int up, int ov, int kw
     dim3 grid((out.H * out.W + 255) / 256, out.Cp >> 3, B);
     ProfScope ps(h, PROF_ELEMWISE, s, 0, (double)B * (out.Cp >> 3) * out.H * out.W * 32 + (double)B * x.C * x.H * x.W);
     stem_unroll_kernel<<<grid, 256, 0, s>>>(x, qt, up, ov, kw, out);
+    h->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
+// Pre-shifted copies for the stem mode of the pair kernel (kernels.cuh: stem_shift).  One thread per (image, plane, row,
+// unit column u): it reads the 15 pixels 8u .. 8u+14 once and writes the 8 windows [8u+s, 8u+s+8) as 128 contiguous bytes.
+__global__ void stem_shift_kernel(Act x, const float *__restrict__ qt, int up, int ov, int uw, int bf16, uint4 *__restrict__ dst, int B)
+{
+    const int S0 = x.H, cx = x.C, planes = cx + (qt ? 2 : 0);
+    const size_t total = (size_t)B * planes * S0 * uw;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int u = (int)(r % uw); r /= uw;
+        const int y = (int)(r % S0); r /= S0;
+        const int pl = (int)(r % planes), n = (int)(r / planes);
+        const float *qrow = (pl >= cx && y >= ov) ? qt + (size_t)n * 64 + ((y - ov) / up) * 8 : nullptr;
+        uint32_t hv[15];
+#pragma unroll
+        for (int e = 0; e < 15; e++) {
+            const int xx = 8 * u + e;
+            float val = 0.f;
+            if (xx < S0) {
+                if (pl < cx) val = load_elem(x, n, pl, y, xx);
+                else if (qrow && xx >= ov) val = qrow[(xx - ov) / up];
+            }
+            uint16_t hi, lo;
+            split16(val, bf16 != 0, hi, lo);
+            hv[e] = (pl == cx + 1) ? lo : hi;          // plane cx: hi half of the qt channel, cx + 1: its lo half
+        }
+#pragma unroll
+        for (int sft = 0; sft < 8; sft++) {
+            uint4 o;
+            o.x = hv[sft] | (hv[sft + 1] << 16); o.y = hv[sft + 2] | (hv[sft + 3] << 16);
+            o.z = hv[sft + 4] | (hv[sft + 5] << 16); o.w = hv[sft + 6] | (hv[sft + 7] << 16);
+            dst[i * 8 + sft] = o;
+        }
+    }
+}
+
+int stem_shift(Handle *h, const Act &x, const float *qt, int up, int ov, int uw, bool bf16, void *dst, int B, cudaStream_t s)
+{
+    if (B <= 0) return PMP_OK;
+    const int planes = x.C + (qt ? 2 : 0);
+    const size_t total = (size_t)B * planes * x.H * uw;
+    const int grid = (int)((total + 255) / 256 < 148 * 64 ? (total + 255) / 256 : 148 * 64);
+    ProfScope ps(h, PROF_ELEMWISE, s, 0, (double)total * 128 + (double)B * x.C * x.H * x.W);
+    stem_shift_kernel<<<grid, 256, 0, s>>>(x, qt, up, ov, uw, bf16 ? 1 : 0, reinterpret_cast<uint4 *>(dst), B);
     h->launches++;
     PMP_CUDA(cudaGetLastError());
     return PMP_OK;

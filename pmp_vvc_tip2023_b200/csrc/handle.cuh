@@ -20,8 +20,15 @@ struct ConvW {
     int sc_cin = 0, sc_cin_pad = 0;
 };
 
+// K-chunk layout of a net's first-layer conv for the pair kernel's stem mode (nets.cu: build_stem_tc)
+struct StemLayout {
+    int planes = 0, nchunk = 0;
+    signed char chunk_plane[8] = {0}, chunk_u0[8] = {0};
+};
+
 struct WeightSet {
     int net = -1;
+    StemLayout stem;
     std::map<std::string, ConvW> convs;     // keyed by reference parameter prefix ("resblock_q1.left.0")
     std::vector<void *> allocs;
 };

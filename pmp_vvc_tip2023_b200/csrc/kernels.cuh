@@ -43,6 +43,11 @@ struct TcConvArgs {
     int pad_t = 0, pad_l = 0;       // input coordinate = output coordinate + tap - pad
     int Ho = 0;                     // output rows (0: same as the input)
     int relu = 0, pool = 1;
+    // first-layer ("stem") mode: the K chunks of the kx-unrolled input are assembled by TMA from the pre-shifted copies
+    // written by stem_shift (layout there); `in` only describes the shape (Cp = 16 * groups, H = source rows, W = out W).
+    const void *stem_src = nullptr;
+    int stem_planes = 0, stem_rows = 0, stem_uw = 0, stem_nchunk = 0;
+    signed char stem_chunk_plane[8] = {0}, stem_chunk_u0[8] = {0};
     int hpool = 0;                  // epilogue takes the horizontal maximum of pixel pairs: `out` is H x W/2 (CTA-pair kernel;
                                     // pool2_split then finishes the 2x2 max-pool with the vertical half)
     double flops_override = 0;      // algorithmic FLOPs per image for the profile (0: from the shapes)
@@ -62,5 +67,9 @@ bool tc_fusion_available();      // the CTA-pair kernel is the active TC path (f
 // U[c*kw + j][y][x] = X[c][y][x + j] (x2 = cat[x, pad_lu(up(qt))] when qt != nullptr): the kx taps of a first-layer conv
 // unrolled into channels so that the tensor-core kernel can run it as a kh x 1 conv.  out: FMT_SPLIT [B, (cx+1?)*kw, S0, S1]
 int stem_unroll(Handle *h, const Act &x, const float *qt, int up, int ov, int kw, const Act &out, int B, cudaStream_t s);
+// 8 pre-shifted 16-bit copies of every source plane of a first-layer conv: dst [B * planes][S0][uw][8 shifts][8 pixels],
+// unit (y, u, s) = pixels 8u+s .. 8u+s+7 of row y (zero beyond the block).  planes = x.C pixel planes, then (qt != nullptr)
+// hi and lo halves of cat's extra channel pad_lu(up(qt)) (Model_QBD.py:130-131).
+int stem_shift(Handle *h, const Act &x, const float *qt, int up, int ov, int uw, bool bf16, void *dst, int B, cudaStream_t s);
 
 }  // namespace pmp

@@ -136,7 +136,42 @@ static int build_stem_tc(WeightSet &ws, int net, const std::vector<ParamSpec> &s
     rc = dev_upload(ws, pp, &cw.w_pair_f16);
     if (rc) return rc;
     pack_tc_pair_weights(wm.data(), cout, cu, kb, 1, cw.cin_pad, cw.cout_pad, true, pp.data());
-    return dev_upload(ws, pp, &cw.w_pair_bf16);
+    rc = dev_upload(ws, pp, &cw.w_pair_bf16);
+    if (rc) return rc;
+
+    // "stem2": the same conv with its K dimension laid out in chunks of 8 unrolled channels = (source plane, 8 consecutive
+    // kx shifts), the form the pair kernel's stem mode assembles by TMA from pre-shifted copies (no unrolled tensor in
+    // HBM).  Source planes: the cin - (q ? 0 : 1) pixel planes, then for the MSBD nets the hi and lo halves of the qt
+    // channel (both multiply the qt channel's weights: W * (hi + lo)).
+    const int cx = q ? cin : cin - 1;
+    StemLayout &sl = ws.stem;
+    sl.planes = cx + (q ? 0 : 2); sl.nchunk = 0;
+    for (int pl = 0; pl < sl.planes; pl++)
+        for (int j0 = 0; j0 < kb; j0 += 8) {
+            if (sl.nchunk >= 8) { set_error("stem layout needs more than 8 K chunks"); return PMP_ERR_UNSUPPORTED; }
+            sl.chunk_plane[sl.nchunk] = (signed char)pl; sl.chunk_u0[sl.nchunk] = (signed char)(j0 / 8); sl.nchunk++;
+        }
+    const int groups2 = (sl.nchunk + 1) / 2, cu2 = 16 * groups2;
+    std::vector<float> wm2((size_t)cout * cu2 * kb, 0.f);
+    for (int c = 0; c < sl.nchunk; c++) {
+        const int src_c = sl.chunk_plane[c] < cx ? sl.chunk_plane[c] : cx;      // both qt planes read the qt channel's weights
+        for (int e = 0; e < 8; e++) {
+            const int j = 8 * sl.chunk_u0[c] + e;
+            if (j >= kb) continue;
+            for (int o = 0; o < cout; o++)
+                for (int ky = 0; ky < kb; ky++)
+                    wm2[((size_t)o * cu2 + (8 * c + e)) * kb + ky] = wm[((size_t)o * cu + (src_c * kb + j)) * kb + ky];
+        }
+    }
+    ConvW &c2 = ws.convs["stem2"];
+    c2.cout = cout; c2.cin = cu2; c2.kh = kb; c2.kw = 1; c2.cin_pad = cu2; c2.cout_pad = pad16(cout);
+    c2.bias = cw.bias;
+    std::vector<uint16_t> p2(tc_pair_packed_elems(cu2, c2.cout_pad, kb, 1));
+    pack_tc_pair_weights(wm2.data(), cout, cu2, kb, 1, cu2, c2.cout_pad, false, p2.data());
+    rc = dev_upload(ws, p2, &c2.w_pair_f16);
+    if (rc) return rc;
+    pack_tc_pair_weights(wm2.data(), cout, cu2, kb, 1, cu2, c2.cout_pad, true, p2.data());
+    return dev_upload(ws, p2, &c2.w_pair_bf16);
 }
 
 int weights_create(Handle *h, int net, const float *const *tensors, const int64_t *numel, int n, int *wset)
@@ -355,6 +390,36 @@ struct Net {
         const uint16_t *wp = (h->tc_dtype == PMP_TC_BF16) ? w->w_tc_bf16 : w->w_tc_f16;
         if (!wp || !tc_supported(w->cin_pad, w->cout_pad, w->kh, 1, out.H, out.W)) return false;
         const size_t mark = off;
+        static const int env_stem2 = [] { const char *e = getenv("PMP_TC_STEM2"); return e ? atoi(e) : 1; }();      // A/B knob
+        const ConvW *w2 = env_stem2 && tc_fusion_available() && !(out.W & 7) ? weights("stem2") : nullptr;
+        if (w2 && ws->stem.nchunk > 0) {
+            // pair kernel's stem mode: 8 pre-shifted 16-bit copies of each source plane (0.08 MB per luma block instead of
+            // a 0.3-0.6 MB unrolled tensor written and read back), the K chunks are assembled by TMA
+            const StemLayout &sl = ws->stem;
+            const int uw = out.W / 8 + (w2->kh > 8 ? 1 : 0);
+            Act cp;
+            cp.fmt = FMT_U8; cp.C = cp.Cp = 1; cp.H = 1; cp.W = 1;
+            cp.bytes = (((size_t)B * sl.planes * x.H * uw * 128) + 1023) & ~(size_t)1023;
+            cp.p = dry ? nullptr : (void *)(h->arena + off);
+            off += cp.bytes;
+            if (off > peak) peak = off;
+            if (!dry) {
+                const bool bf = h->tc_dtype == PMP_TC_BF16;
+                rc = stem_shift(h, x, qt, up, ov, uw, bf, cp.p, B, s);
+                TcConvArgs a;
+                a.in.fmt = FMT_SPLIT; a.in.C = w2->cin; a.in.Cp = w2->cin_pad; a.in.H = x.H; a.in.W = out.W; a.in.bf16 = bf; a.in.p = cp.p;
+                a.out = out; a.bias = w2->bias;
+                a.w_pair = bf ? w2->w_pair_bf16 : w2->w_pair_f16;
+                a.w = a.w_pair;         // unused: stem mode runs on the pair kernel only
+                a.cin_pad = w2->cin_pad; a.cout_pad = w2->cout_pad; a.kh = w2->kh; a.kw = 1; a.pad_t = 0; a.pad_l = 0;
+                a.Ho = out.H; a.relu = 1; a.pool = 1; a.flops_override = flops_per_image;
+                a.stem_src = cp.p; a.stem_planes = sl.planes; a.stem_rows = x.H; a.stem_uw = uw; a.stem_nchunk = sl.nchunk;
+                for (int c = 0; c < 8; c++) { a.stem_chunk_plane[c] = sl.chunk_plane[c]; a.stem_chunk_u0[c] = sl.chunk_u0[c]; }
+                if (!rc) rc = conv_tc(h, a, B, s);
+            }
+            off = mark;
+            return true;
+        }
         Act u = alloc(w->cin, x.H, out.W, FMT_SPLIT);
         if (!dry) {
             rc = stem_unroll(h, x, qt, up, ov, w->kh, u, B, s);
