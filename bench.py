@@ -307,8 +307,16 @@ def main():
     if not args.no_profile and prof.get(dom, {}).get("ms", 0) > 0:
         p = prof[dom]
         ach = p["flops"] / (p["ms"] * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01b_traffic.json")
+        if dom == "conv_tc" and os.path.exists(tpath):
+            # dram__bytes_read+write per conv_tc launch from an ncu pass over 480-block launches (committed summary),
+            # scaled to this run's blocks per launch: HBM bytes per launch of the dominant kernel class
+            tj = json.load(open(tpath))
+            traffic = tj["conv_tc_dram_bytes_per_launch_per_block"] * min(args.chunk, FRAMES * (HEIGHT // 64) * (WIDTH // 64))
+            traffic_src = tj["source"] + "; scaled from 480 to %d blocks per launch" % min(args.chunk, FRAMES * (HEIGHT // 64) * (WIDTH // 64))
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_sustained"], "traffic": None,
+                "frac": ach / pk["bf16_sustained"], "traffic": traffic, "traffic_src": traffic_src,
                 "peak_src": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches": p["launches"], "avg_launch_ms": p["ms"] / max(p["launches"], 1),
                 "algorithmic_flops_per_launch": p["flops"] / max(p["launches"], 1),
