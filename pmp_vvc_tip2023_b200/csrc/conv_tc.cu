@@ -1,13 +1,14 @@
-// TC engine: stride-1 "same" convolution (1x1 / 3x3 / 5x5) as an implicit GEMM on the 5th-gen tensor cores.
+// TC engine: stride-1 "same" convolution (1x1 / 3x3 / 5x5, and the kh x 1 form of the first-layer convs) as an implicit
+// GEMM on the 5th-gen tensor cores.
 //
 //   D[pixels, cout] += A[pixels, cin] * W[cin, cout]   per filter tap, fp32 accumulation in TMEM.
 //
 // Split precision (single-pass 16-bit operands miss the 1e-2 parity bar): activations and
 // weights are stored as hi + lo 16-bit pairs and three products are accumulated,
 //   a_hi*w_hi + a_hi*w_lo + a_lo*w_hi        (error ~ a_lo*w_lo ~ 2^-22 relative with fp16),
-// as three tcgen05.mma (N = Cout) per K=16 step into the same Cout accumulator columns.  (Stacking [w_hi | w_lo] along
-// N saves shared-memory operand reads but needs 2*Cout columns per M-tile; measured, the kernel is bound by issue
-// latency and the TMEM drain rather than by operand bandwidth, so the columns are spent on double buffering instead.)
+// either as three tcgen05.mma with N = Cout into the same columns (unstacked) or as a_hi x [w_hi | w_lo] (N = 2*Cout) plus
+// a_lo x w_hi (N = Cout) with the epilogue adding the column halves (stacked: fewer shared-memory operand reads, twice the
+// TMEM columns; the default wherever the layer is not bandwidth-bound, see tc_pair_stacked_layout).
 //
 // Tiling ("halo-resident linear tile"): a CTA tile is up to 4 M-tiles of 128 consecutive positions of ONE image, counted on
 // the zero-padded pitch P = W + k - 1.  One TMA box per 16-channel group (8 x P x rows x 4 planes) brings the halo tile
@@ -15,12 +16,19 @@
 // out-of-bounds zero fill providing the convolution's zero padding.  Because the tile is linear on pitch P, the A
 // operand of filter tap (ky,kx) is the same descriptor advanced by (ky*P + kx)*16 bytes; positions that fall into the
 // P-W pad columns compute garbage that the epilogue drops (W/P = 94..97 % efficiency).  Weights stream through a
-// shared-memory ring, one (tap, channel-group) slab [2][N][8] per stage via cp.async.bulk, pre-packed on the host.
+// shared-memory ring of pre-packed slabs.
 //
-// Warp roles (448 threads, persistent grid): warp 0 = weight producer, warp 1 = activation producer + TMEM owner,
+// Kernels:
+//   conv_tc_pair_kernel  the production path (every layer, every batch size): 2-CTA clusters issuing cta_group::2 MMAs
+//                        with M = 256 over two images, row-granular weight stages, a lean warp-uniform issue loop
+//                        (pair_issuer), accumulator and activation slot rings, fused 1x1 shortcut (second input tensor),
+//                        fused horizontal max-pool, TMA-assembled first-layer ("stem") mode, programmatic dependent launch.
+//   conv_tc_kernel       the first-generation single-CTA kernel (per-tap stages), kept as the PMP_TC_PAIR=0 / self-test
+//                        A-B reference; same arithmetic per accumulator, so both produce the same bits.
+// Warp roles in both (448 threads, persistent grid): warp 0 = weight producer, warp 1 = activation producer + TMEM owner,
 // warps 2-5 = MMA issuers (one per M-tile), warps 6-13 = epilogue (TMEM -> registers -> bias / residual add / ReLU /
-// attention product -> hi/lo split -> coalesced 16-byte stores).  Two kernels: conv_tc_kernel (one CTA per SM) and
-// conv_tc_pair_kernel (cta_group::2 CTA pairs, the default whenever the batch has at least two images).
+// attention product / pair maximum -> hi/lo split -> coalesced 16-byte stores).
+// What was measured and why each piece exists: profiles/r01_conv_tc_ncu_summary.md, profiles/r01b_conv_tc_pair_summary.md.
 #include "handle.cuh"
 #include "kernels.cuh"
 
