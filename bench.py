@@ -336,7 +336,12 @@ def main():
                    "d2h_bytes_per_step": int(sum(t.numel() for t in host_out.values())),
                    "ms_per_step": ms_e2e / args.steps},
            "roofline": roof,
-           "kernel_classes_ms_per_step": {k: p["ms"] / args.steps for k, p in prof.items() if p["launches"]}}
+           "kernel_classes_ms_per_step": {k: p["ms"] / args.steps for k, p in prof.items() if p["launches"]},
+           # the integer / element-wise kernel classes against the HBM roofline: algorithmic bytes
+           # over the CUDA-event time of their launches in the profiled pass
+           "hbm_kernels": {k: {"achieved_gbs": p["bytes"] / (p["ms"] * 1e-3) / 1e9, "peak_gbs": pk["hbm_gbs"],
+                               "frac": p["bytes"] / (p["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"], "launches": p["launches"]}
+                           for k, p in prof.items() if p["launches"] and p["bytes"] > 0 and p["ms"] > 0 and not k.startswith("conv")}}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample()
     print(json.dumps(out))
