@@ -214,3 +214,25 @@ def test_bf16_split_engine_within_tolerance(comp, qp):
         assert err_q <= 1e-2 and err_b <= 1e-2, (err_q, err_b)
     finally:
         h.set_engine(_lib.ENGINE_TC, _lib.TC_FP16)
+
+
+def test_predict_frames_host_out_matches_device_results():
+    """The public API's overlapped device->host copies (side stream, one per finished component) deliver exactly the
+    vectors the call returns on the device, for several QPs and repeated calls into the same pinned buffers."""
+    y, u, v = cases.pipeline_frames()
+    pp = PartitionPredictor(0, engine="tc", chunk=5)
+    qps = (27, 32)
+    for comp in ("Luma", "Chroma"):
+        for qp in qps:
+            pp.load_state_dicts(comp, qp, load_reference_pkl(os.path.join(ROOT, "trained_models", "%s_Q_%d.pkl" % (comp, qp))),
+                                synth.seeded_state_dict(comp + "_MSBD", cases.msbd_seed(comp, qp)))
+    ref = pp.predict_frames(y, u, v, qps=qps)
+    host = {k: torch.empty(t.shape, dtype=torch.int8).pin_memory() for k, t in ref.items()}
+    for _ in range(2):
+        for t in host.values():
+            t.fill_(-7)
+        res = pp.predict_frames(y, u, v, qps=qps, host_out=host)
+        pp.synchronize()
+        for k in ref:
+            assert torch.equal(res[k].cpu(), ref[k].cpu())
+            assert torch.equal(host[k], ref[k].cpu()), k
