@@ -1,5 +1,6 @@
 """CPU accuracy study for the next step of the split-precision scheme: which operand formats the two
-correction products a_hi*w_lo and a_lo*w_hi tolerate.  Emulates per-conv operand rounding with fp32 results on the trained Q
+correction products a_hi*w_lo and a_lo*w_hi tolerate, and what Winograd F(2x2,3x3) on split operands (2.25x fewer MACs for
+the 3x3 layers; "wino3-*": every 3x3 "same" conv through the transform, the rest direct fp16x3) costs in accuracy.  Emulates per-conv operand rounding with fp32 results on the trained Q
 nets (the MSBD *.pkl are not in this checkout) over synthetic textured blocks and prints the max-abs error of the 8x8 QT map
 against fp64 convolutions of the unrounded operands.  Pure PyTorch on the CPU; no library code involved.
 
@@ -38,17 +39,40 @@ def r8(x, fmt, scaled=True):
     return y / s
 
 
+# Winograd F(2x2, 3x3) (Lavin & Gray): Y = A^T [(G g G^T) . (B^T d B)] A per 4x4 input tile, 16 multiplies per 4 outputs
+_BT = torch.tensor([[1, 0, -1, 0], [0, 1, 1, 0], [0, -1, 1, 0], [0, 1, 0, -1]], dtype=torch.float64)
+_G = torch.tensor([[1, 0, 0], [0.5, 0.5, 0.5], [0.5, -0.5, 0.5], [0, 0, 1]], dtype=torch.float64)
+_AT = torch.tensor([[1, 1, 1, 0], [0, 1, -1, -1]], dtype=torch.float64)
+
+
+def winograd3x3(x, w, rnd):
+    """3x3 'same' conv through F(2x2,3x3) with both transformed operands split into hi + lo (rnd) and three products."""
+    B, C, H, W = x.shape
+    co = w.shape[0]
+    tiles = F.unfold(F.pad(x, (1, 1, 1, 1)), kernel_size=4, stride=2).view(B, C, 16, -1)          # [B, C, 16, T]
+    V = torch.einsum("ef,bcft->bcet", torch.kron(_BT, _BT), tiles).float().double()                 # fp32 transform results
+    U = torch.einsum("ef,ocf->oce", torch.kron(_G, _G), w.reshape(co, C, 9))                        # host side, exact
+    Vh, Uh = rnd(V), rnd(U)
+    Vl, Ul = rnd(V - Vh), rnd(U - Uh)
+    M = torch.einsum("oce,bcet->boet", Uh, Vh) + torch.einsum("oce,bcet->boet", Ul, Vh) + torch.einsum("oce,bcet->boet", Uh, Vl)
+    M = M.float().double()                                                                          # fp32 accumulators
+    Y = torch.einsum("ye,boet->boyt", torch.kron(_AT, _AT), M)                                      # [B, co, 4, T]
+    return F.fold(Y.reshape(B, co * 4, -1), (H, W), kernel_size=2, stride=2)
+
+
 def make_conv(scheme):
     def conv(x, w, b=None, padding=0):
         x = x.double(); w = w.double()
-        if scheme == "exact":
+        if scheme.startswith("wino3") and w.shape[2] == 3 and w.shape[3] == 3 and padding == 1:
+            out = winograd3x3(x, w, rbf if "bf16" in scheme else r16)
+        elif scheme == "exact":
             out = F.conv2d(x, w, padding=padding)
         else:
             rnd = rbf if scheme.startswith("bf16") else r16
             xh, wh = rnd(x), rnd(w)
             xl, wl = rnd(x - xh), rnd(w - wh)
             out = F.conv2d(xh, wh, padding=padding)
-            if scheme in ("fp16x3", "bf16x3"):
+            if scheme in ("fp16x3", "bf16x3", "wino3-fp16x3", "wino3-bf16x3"):
                 out = out + F.conv2d(xh, wl, padding=padding) + F.conv2d(xl, wh, padding=padding)
             elif scheme.startswith("mixed"):            # mixed-<fmt>[-noscale]: corrections with 8-bit operands
                 fmt = scheme.split("-")[1]
@@ -95,7 +119,7 @@ def main():
     luma_x = torch.from_numpy(by.astype(np.float32)).unsqueeze(1)
     chroma_x = torch.cat([F.max_pool2d(luma_x, 2), torch.from_numpy(bu.astype(np.float32)).unsqueeze(1),
                           torch.from_numpy(bv.astype(np.float32)).unsqueeze(1)], 1)
-    schemes = ["fp16x1", "bf16x3", "fp16x3", "mixed-e4m3", "mixed-e4m3-noscale", "mixed-e5m2"]
+    schemes = ["fp16x1", "bf16x3", "fp16x3", "mixed-e4m3", "mixed-e4m3-noscale", "mixed-e5m2", "wino3-fp16x3", "wino3-bf16x3"]
     print("max-abs / mean-abs error of the QT map vs exact (fp64 convs), %d blocks; parity bar 1e-2" % n)
     for comp, x in (("Luma", luma_x), ("Chroma", chroma_x)):
         for qp in (22, 37):
