@@ -886,9 +886,7 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
     const uint32_t peer_wempty = mapa_cluster(b.wempty, 1), peer_aempty = mapa_cluster(b.aempty, 1), peer_acc = mapa_cluster(b.acc, 1);
     const int KH = p.kh, P = p.P, NS = p.nstages, G = p.groups;
     long long st_a = 0, st_b = 0, st_c = 0;
-    // stems: 8-bit pixels (and the pre-split qt planes) are exact in 16 bits.  PMP_TC_DBG bit 7 drops the a_lo product
-    // everywhere: a timing/power experiment (wrong results) that shows how much of the power-capped step is tensor energy
-    const bool hi_only = p.stem != 0 || (p.dbg & 128) != 0;
+    const bool hi_only = p.stem != 0;            // stems: 8-bit pixels (and the pre-split qt planes) are exact in 16 bits
     const int G2 = p.groups2;                    // fused 1x1 shortcut: extra channel groups of a second input, centre tap only
     const uint32_t ASLOTS = (uint32_t)p.aslots, ctr16 = (uint32_t)(p.pady * p.P + p.padx);
     uint32_t s = 0, ph = 0, idx = 0, as = 0, aph = 0;   // weight stage / activation slot of the ring and their parities
@@ -1254,7 +1252,7 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         p.stem_chunk_plane[c] = stem ? a.stem_chunk_plane[src] : 0;
         p.stem_chunk_u0[c] = stem ? a.stem_chunk_u0[src] : 0;
     }
-    static const int env_dbg = [] { const char *e = getenv("PMP_TC_DBG"); return e ? atoi(e) : 0; }();   // timing experiments only
+    static const int env_dbg = [] { const char *e = getenv("PMP_TC_DBG"); return e ? atoi(e) : 0; }();   // bit 6: per-role stall counters
     p.dbg = env_dbg;
     if (!h->tc_attr_set) {          // function attributes are per device: one handle per device
         PMP_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
