@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PMP_B200_VERSION 100 /* 0.1.0 */
+#define PMP_B200_VERSION 200 /* 0.2.0 */
 
 typedef struct pmp_handle pmp_handle;
 
@@ -51,11 +51,18 @@ enum pmp_in_dtype { PMP_IN_U8 = 0, PMP_IN_F32 = 1 };
 int pmp_version(void);
 const char *pmp_last_error(void);
 
-/* Lifetime.  pmp_create binds to `device`, creates no streams of its own. */
+/* Lifetime.  pmp_create binds to `device`, creates no streams of its own.  A new handle runs PMP_ENGINE_TC / PMP_TC_FP16. */
 int pmp_create(int device, pmp_handle **out);
 void pmp_destroy(pmp_handle *h);
 int pmp_set_engine(pmp_handle *h, int engine, int tc_dtype);
 int pmp_get_engine(pmp_handle *h);
+/* Tolerance of the near-threshold report in pmp_run_component / pmp_map2partition flags bits 1..3 (default 1e-2, the
+ * north-star parity bar on map values). */
+int pmp_set_near_tol(pmp_handle *h, float near_tol);
+/* Sticky fp16 range guard of the TC engine: number of epilogue threads that produced an activation beyond +-65504 with
+ * fp16 operands since creation / the last reset (the hi/lo split clamps there, so a non-zero count means wrong results:
+ * switch the handle to PMP_TC_BF16).  Synchronises the device. */
+int pmp_saturation_count(pmp_handle *h, long long *count_host, int reset);
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 long long pmp_launch_count(pmp_handle *h);
 /* Name/elapsed-ms of per-kernel-class CUDA-event timers (enabled with pmp_profile(h,1)); see bench.py. */
@@ -96,11 +103,20 @@ int pmp_qt_postprocess(pmp_handle *h, const float *qt, int B, float *out_f32, ui
  * qt_u8 [B,64] values 0..3 (post-processed), bt/dire [B,3,16,16] f32 (un-rounded), chroma_factor 1|2.
  * hor/ver [B,16,16] u8 {0,1}; dire_out [B,3,16,16] i8 {-1,0,1}; flags [B] u32 (may be NULL):
  * bit0 = the argmin over candidate partitions had a runner-up within the float32 evaluation noise
- * of the reference (result may legitimately differ from a float32 evaluation), bits 8.. = number
- * of MTT regions decoded. */
+ * of the reference (result may legitimately differ from a float32 evaluation); bit1 = a depth value lies
+ * within near_tol of a rounding threshold k+0.5 (np.round, Map2Partition.py:104); bit2 = a direction
+ * value lies within near_tol of +-0.5 (th_round, :30-35,:105); bit3 = a 2x2-pooled raw qt value lies
+ * within near_tol of 0.5/1.5/2.5 (Metrics.py:631-632; only when qt_raw is given); bits 8.. = number of
+ * MTT regions decoded.  near_tol = the handle's (pmp_set_near_tol). */
 int pmp_map2partition(pmp_handle *h, const uint8_t *qt_u8, const float *bt, const float *dire, int B,
                       int chroma_factor, uint8_t *hor, uint8_t *ver, int8_t *dire_out, uint32_t *flags,
                       void *stream);
+/* Same with the constructor thresholds of Map_to_Partition (Map2Partition.py:100: lamb1..lamb5 as 5 doubles, NULL = the
+ * reference defaults 0.7, 0.7, 1.5, 0.3, 0.7), the raw qt maps [B,64] f32 for flags bit3 (may be NULL) and an explicit
+ * near_tol. */
+int pmp_map2partition_ex(pmp_handle *h, const uint8_t *qt_u8, const float *bt, const float *dire, int B,
+                         int chroma_factor, const double *lamb, const float *qt_raw, float near_tol, uint8_t *hor,
+                         uint8_t *ver, int8_t *dire_out, uint32_t *flags, void *stream);
 /* pmp_assemble_frames == the scatter + per-frame vector order of get_sequence_partition_for_VTM
  * (Map2Partition.py:389-412).  Blocks are frame-major raster (bh x bw per frame).  out: per frame
  * hor[R*C] | ver[R*C] | qt[(R/2)*(C/2)] | dire[3*R*C] as int8, R=16*bh, C=16*bw; frames contiguous.
@@ -141,6 +157,22 @@ int pmp_run_component(pmp_handle *h, int wset_q, int wset_msbd, int luma, const 
  * fused into the conv epilogue (checked against the exact conv with fused pooling; excludes bit2). */
 int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, int hw, int batch, int flags,
                       double *max_err, double *ref_absmax, double *ms_tc, double *ms_simt);
+
+/* Test hook: one TC-engine convolution (ResidualBlock conv variants of Model_QBD.py:23-44) on caller-supplied fp32
+ * data, so that tests can check the tcgen05 kernels against an independent convolution (torch F.conv2d on the CPU).
+ * in [B,cin,hw,hw], res/mul [B,cout,..] (may be NULL), in2 [B,cin2,hw,hw] (fused 1x1 shortcut input, may be NULL): DEVICE
+ * fp32 NCHW; w_host [cout,cin,k,k], w_sc_host [cout,cin2]: HOST fp32.  flags: bit0 ReLU, bit3 bf16 operands, bit18 2x2
+ * max-pool.  out [B,cout,Ho,Wo] device fp32.  Synchronises the stream. */
+int pmp_debug_conv(pmp_handle *h, const float *in, const float *w_host, const float *res, const float *mul,
+                   const float *in2, const float *w_sc_host, int cin, int cout, int ksize, int hw, int batch, int cin2,
+                   int flags, float *out, void *stream);
+
+/* Test hook: only the first-layer conv(s) of weight set `wset`'s net (conv_q1 with padding_rb, Model_QBD.py:79-80; or
+ * conv_b1_1..3 on cat[x, pad_lu(up(qt))] concatenated, :130-135) through the TC engine's stem path (TMA-assembled K
+ * chunks), bias + ReLU applied.  qt [B,1,8,8] f32 for the MSBD nets, NULL for the Q nets.  out [B,32,S,S] device fp32
+ * (S = 64 luma / 32 chroma). */
+int pmp_debug_stem(pmp_handle *h, int wset, const void *blocks, int in_dtype, const float *qt, int B, float *out,
+                   void *stream);
 
 /* Debug/profiling aid: per-CTA barrier-stall cycle counters of the CTA-pair conv kernel (filled when the environment
  * variable PMP_TC_DBG has bit 6 set; 16 uint64 per CTA, see conv_tc.cu).  n = number of uint64 to copy (<= 2560). */

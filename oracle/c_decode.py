@@ -23,6 +23,7 @@ def lib():
         build()
         _lib = ctypes.CDLL(_SO)
         _lib.oracle_map_to_partition.restype = ctypes.c_int
+        _lib.oracle_map_to_partition_lamb.restype = ctypes.c_int
     return _lib
 
 
@@ -30,8 +31,9 @@ def _p(a, t):
     return a.ctypes.data_as(ctypes.POINTER(t))
 
 
-def map_to_partition_batch(qt, bt, dire, chroma_factor, return_leaves=False):
-    """qt [n,8,8] f32 (ints), bt/dire [n,3,16,16] f32 -> hor,ver [n,16,16] u8, dire [n,3,16,16] i8."""
+def map_to_partition_batch(qt, bt, dire, chroma_factor, return_leaves=False, lamb=(0.7, 0.7, 1.5, 0.3, 0.7)):
+    """qt [n,8,8] f32 (ints), bt/dire [n,3,16,16] f32 -> hor,ver [n,16,16] u8, dire [n,3,16,16] i8.
+    lamb: the constructor thresholds lamb1..lamb5 (Map2Partition.py:100)."""
     qt = np.ascontiguousarray(qt, np.float32).reshape(-1, 64)
     n = qt.shape[0]
     bt = np.ascontiguousarray(bt, np.float32).reshape(n, 768)
@@ -40,9 +42,10 @@ def map_to_partition_batch(qt, bt, dire, chroma_factor, return_leaves=False):
     ver = np.zeros((n, 16, 16), np.uint8)
     dout = np.zeros((n, 3, 16, 16), np.int8)
     leaves = np.zeros(n, np.int64)
-    bad = lib().oracle_map_to_partition(
+    lam = (ctypes.c_double * 5)(*[float(x) for x in lamb])
+    bad = lib().oracle_map_to_partition_lamb(
         _p(qt, ctypes.c_float), _p(bt, ctypes.c_float), _p(dire, ctypes.c_float), ctypes.c_int(n),
-        ctypes.c_int(chroma_factor), _p(hor, ctypes.c_uint8), _p(ver, ctypes.c_uint8),
+        ctypes.c_int(chroma_factor), lam, _p(hor, ctypes.c_uint8), _p(ver, ctypes.c_uint8),
         _p(dout, ctypes.c_int8), _p(leaves, ctypes.c_long))
     if bad:
         raise RuntimeError("oracle leaf cap exceeded on %d blocks" % bad)

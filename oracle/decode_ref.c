@@ -34,6 +34,7 @@ typedef struct {
     float rbt[3][256];    /* np.round */
     int8_t rdire[3][256]; /* th_round(.,0.5) */
     int cf;
+    double lamb[5];       /* lamb1..lamb5 of the constructor (Map2Partition.py:100,:118-122); Python floats = doubles */
     uint8_t par[2][17][17];
     int8_t out_dire[3][256];
     /* search state */
@@ -107,11 +108,11 @@ static int candidate_modes(const Ctx *c, Rect r, const int8_t *cur, int d, int *
             if (c->rdire[d][k] == -1) nv++;
         }
     modes[0] = 0;
-    if ((double)zero2 >= 0.7 * r.h * r.w) return 1;
+    if ((double)zero2 >= c->lamb[0] * r.h * r.w) return 1;
     int direction = 0;
-    if ((double)(nv + nh) >= 0.7 * r.h * r.w) {
-        if ((double)nh >= 1.5 * nv) direction = 1;
-        else if ((double)nv >= 1.5 * nh) direction = 2;
+    if ((double)(nv + nh) >= c->lamb[1] * r.h * r.w) {
+        if ((double)nh >= c->lamb[2] * nv) direction = 1;
+        else if ((double)nv >= c->lamb[2] * nh) direction = 2;
     }
     int nm = 1;
     (void)n;
@@ -133,7 +134,7 @@ static int candidate_modes(const Ctx *c, Rect r, const int8_t *cur, int d, int *
                     if (cmp == 0.f) zero++;
                 }
             int np_ = sub[s].h * sub[s].w;
-            if (!((double)minus < np_ * 0.3 && (double)zero > np_ * 0.7)) ok = 0;
+            if (!((double)minus < np_ * c->lamb[3] && (double)zero > np_ * c->lamb[4])) ok = 0;
         }
         if (ok) modes[nm++] = mode;
     }
@@ -230,8 +231,18 @@ static void decode_qt(Ctx *c, const float *qt, int depth, int qx, int qy)
  * Outputs hor/ver [n][256] u8, dire_out [n][3][256] i8.  Returns the number of blocks
  * whose search overflowed LEAF_CAP (0 normally); leaves_out (optional) gets the leaf count
  * per block. */
+int oracle_map_to_partition_lamb(const float *qt, const float *bt, const float *dire, int n, int chroma_factor,
+                                 const double *lamb, uint8_t *hor, uint8_t *ver, int8_t *dire_out, long *leaves_out);
+
 int oracle_map_to_partition(const float *qt, const float *bt, const float *dire, int n, int chroma_factor,
                             uint8_t *hor, uint8_t *ver, int8_t *dire_out, long *leaves_out)
+{
+    static const double def[5] = {0.7, 0.7, 1.5, 0.3, 0.7};      /* Map2Partition.py:100 */
+    return oracle_map_to_partition_lamb(qt, bt, dire, n, chroma_factor, def, hor, ver, dire_out, leaves_out);
+}
+
+int oracle_map_to_partition_lamb(const float *qt, const float *bt, const float *dire, int n, int chroma_factor,
+                                 const double *lamb, uint8_t *hor, uint8_t *ver, int8_t *dire_out, long *leaves_out)
 {
     int bad = 0;
     static _Thread_local Ctx ctx;
@@ -241,6 +252,7 @@ int oracle_map_to_partition(const float *qt, const float *bt, const float *dire,
         c->obt = bt + (size_t)b * 768;
         c->odire = dire + (size_t)b * 768;
         c->cf = chroma_factor;
+        for (int k = 0; k < 5; k++) c->lamb[k] = lamb[k];
         for (int k = 0; k < 768; k++) {
             float v = c->obt[k];
             (&c->rbt[0][0])[k] = rintf(v);                      /* np.round: half to even */

@@ -61,7 +61,8 @@ def child_depth_increment(mode, idx):
 
 
 class DecodeRef:
-    def __init__(self, qt_map, msbt_map, msdire_map, chroma_factor):
+    def __init__(self, qt_map, msbt_map, msdire_map, chroma_factor, lamb=(LAMB1, LAMB2, LAMB3, LAMB4, LAMB5)):
+        self.lamb1, self.lamb2, self.lamb3, self.lamb4, self.lamb5 = lamb       # :118-122
         self.qt = qt_map
         self.ori_bt = msbt_map
         self.ori_dire = msdire_map
@@ -74,16 +75,16 @@ class DecodeRef:
     # --- :140-201 ---------------------------------------------------------
     def candidate_modes(self, x, y, h, w, cur_bt, d):
         cmp2 = self.rbt[2, x:x + h, y:y + w] - cur_bt[x:x + h, y:y + w]
-        if np.count_nonzero(cmp2 == 0) >= LAMB1 * h * w:
+        if np.count_nonzero(cmp2 == 0) >= self.lamb1 * h * w:
             return [0]
         reg = self.rdire[d, x:x + h, y:y + w]
         n_hor = np.count_nonzero(reg == 1)
         n_ver = np.count_nonzero(reg == -1)
         direction = 0
-        if (n_ver + n_hor) >= LAMB2 * h * w:
-            if n_hor >= LAMB3 * n_ver:
+        if (n_ver + n_hor) >= self.lamb2 * h * w:
+            if n_hor >= self.lamb3 * n_ver:
                 direction = 1
-            elif n_ver >= LAMB3 * n_hor:
+            elif n_ver >= self.lamb3 * n_hor:
                 direction = 2
         cf = self.cf
         kept = [0]
@@ -103,7 +104,7 @@ class DecodeRef:
                 n_minus = np.count_nonzero(cmpd < 0)
                 n_zero = np.count_nonzero(cmpd == 0)
                 n = sh * sw
-                if not (n_minus < n * LAMB4 and n_zero > n * LAMB5):
+                if not (n_minus < n * self.lamb4 and n_zero > n * self.lamb5):
                     ok = False          # reference keeps counting; result is the same
             if ok:
                 kept.append(mode)
@@ -174,12 +175,12 @@ class DecodeRef:
         return self.par_vec[0][:16, :16], self.par_vec[1][:16, :16], self.out_dire
 
 
-def map_to_partition(qt_map, bt_map, dire_map, chroma_factor):
-    """Restates Map2Partition.map_to_parititon (:368-373).
+def map_to_partition(qt_map, bt_map, dire_map, chroma_factor, lamb=(LAMB1, LAMB2, LAMB3, LAMB4, LAMB5)):
+    """Restates Map2Partition.map_to_parititon (:368-373); ``lamb`` = the Map_to_Partition constructor thresholds (:100).
 
     qt_map [8,8] (integers 0..3 in any dtype), bt_map/dire_map [3,16,16] float32.
     Returns (hor[16,16] u8, ver[16,16] u8, dire[3,16,16] i8)."""
-    return DecodeRef(qt_map, bt_map, dire_map, chroma_factor).run()
+    return DecodeRef(qt_map, bt_map, dire_map, chroma_factor, lamb).run()
 
 
 def sequence_partition(qt_map, bt_map, dire_map, is_luma, frm_num, frm_width, frm_height):

@@ -55,6 +55,27 @@ def gen_decode():
     np.savez_compressed(os.path.join(OUT, "decode_golden.npz"), **res)
 
 
+def gen_decode_lamb():
+    """Map_to_Partition with non-default constructor thresholds lamb1..lamb5 (Map2Partition.py:100)."""
+    res = {}
+    allc = cases.decode_cases()
+    for tag, lamb in cases.LAMB_SETS.items():
+        for fam in cases.LAMB_FAMILIES:
+            qt, bt, dire, cf = allc[fam]
+            n = cases.LAMB_BLOCKS
+            hor = np.zeros((n, 16, 16), np.uint8)
+            ver = np.zeros((n, 16, 16), np.uint8)
+            dout = np.zeros((n, 3, 16, 16), np.int8)
+            for b in range(n):
+                par, d = RefM2P.Map_to_Partition(qt[b], bt[b], dire[b], cf, *lamb).get_partition()
+                hor[b], ver[b], dout[b] = par[0][:16, :16], par[1][:16, :16], d
+            res["%s_%s_hor" % (tag, fam)] = np.packbits(hor.reshape(n, -1), axis=1)
+            res["%s_%s_ver" % (tag, fam)] = np.packbits(ver.reshape(n, -1), axis=1)
+            res["%s_%s_dire" % (tag, fam)] = dout
+            print("decode lamb", tag, fam, "edges", hor.mean())
+    np.savez_compressed(os.path.join(OUT, "decode_lamb_golden.npz"), **res)
+
+
 def gen_postproc():
     q = cases.postproc_inputs()
     out = RefMetrics.eli_structual_error(torch.from_numpy(q.copy())).numpy()
@@ -137,9 +158,11 @@ def gen_demo_fixture():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["decode", "postproc", "nets", "pipeline", "demo"]
+    which = sys.argv[1:] or ["decode", "decode_lamb", "postproc", "nets", "pipeline", "demo"]
     if "decode" in which:
         gen_decode()
+    if "decode_lamb" in which:
+        gen_decode_lamb()
     if "postproc" in which:
         gen_postproc()
     if "nets" in which:

@@ -9,7 +9,6 @@ ranges, one worker thread + handle per GPU, and the per-GPU text segments are co
 """
 import argparse
 import os
-import threading
 import time
 
 import numpy as np
@@ -65,8 +64,9 @@ def output_block_yuv(file_path, width, height, block_size, in_overlap, numfrm, S
     if block_size != 64 or in_overlap != 4:
         raise NotImplementedError("the nets are defined for block_size=64, in_overlap=4 (Inference_QBD.py:190)")
     y, u, v = import_yuv420(file_path, width, height, numfrm, SubSampleRatio, is10bit=is10bit)
-    pp = PartitionPredictor(torch.cuda.current_device(), engine="simt")
-    lb, cb = pp.cut(y, u, v)
+    from . import ops
+    dev = torch.device("cuda", torch.cuda.current_device())
+    lb, cb = ops.cut_blocks(*(torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a).to(dev) for a in (y, u, v)))
     block_y = lb[:, 0].cpu().numpy()
     block_u, block_v = cb[:, 1].cpu().numpy(), cb[:, 2].cpu().numpy()
     if save_path is not None:
@@ -88,16 +88,47 @@ def _parse_cfg(path):
     return seq_path, is10bit
 
 
+def _predict_shard(pred, y, u, v, qps):
+    """One GPU's frame range: cut once, then per (component, QP) the nets + post-process + decode + frame assembly
+    (timed with CUDA events, the counterpart of the reference's per-(QP, comp) inference clock, Inference_QBD.py:210-227)
+    and the text formatting + device->host copy (wall clock; the reference's post-process clock, :229-241).
+    Returns ({(comp, qp): bytes}, {(comp, qp): (net_s, post_s)}, counts)."""
+    from . import ops
+    texts, times = {}, {}
+    f, hgt, wid = y.shape
+    bh, bw = hgt // 64, wid // 64
+    dev = pred.device
+    with torch.cuda.device(dev):
+        lb, cb = pred.cut(y, u, v)
+        for comp in COMPS:
+            blocks = lb if comp == "Luma" else cb
+            for qp in qps:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                vals = pred.predict_blocks(comp, qp, blocks, f, bh, bw)
+                e1.record()
+                e1.synchronize()
+                t0 = time.time()
+                texts[(comp, qp)] = ops.format_text(vals, handle=pred.handle).cpu().numpy().tobytes()
+                times[(comp, qp)] = (e0.elapsed_time(e1) * 1e-3, time.time() - t0)
+        counts = pred.counts()
+    return texts, times, counts
+
+
 @torch.no_grad()
 def inference_VVC_seqs(args):
+    from concurrent.futures import ThreadPoolExecutor
     save_dir = os.path.join(args.outDir, args.jobID, "PartitionMat")
     os.makedirs(save_dir, exist_ok=True)
     ss = getattr(args, "ssRatio", SSRatio)
     gpus = max(1, min(getattr(args, "gpus", 1), torch.cuda.device_count()))
     model_dir = getattr(args, "modelDir", "./CTU_Models/")
     missing_bd = getattr(args, "missingBD", "error")
+    qps = (22, 27, 32, 37)
     names, paths, widths, heights, frmnums, subs, _ = load_sequences_info(getattr(args, "seqInfo", "Training_Sequences.txt"), ss)
-    preds = [PartitionPredictor(g, engine=getattr(args, "engine", "tc"), chunk=max(args.batchSize, 256)) for g in range(gpus)]
+    preds = [PartitionPredictor(g, engine=getattr(args, "engine", "tc"), chunk=max(args.batchSize, 256),
+                                near_tol=getattr(args, "nearTol", 1e-2), tc_dtype=getattr(args, "tcDtype", "fp16"))
+             for g in range(gpus)]
     for p in preds:
         p.load_pkls(model_dir, missing_bd=missing_bd)
     nseq = args.seqNum
@@ -117,32 +148,34 @@ def inference_VVC_seqs(args):
         nf = y.shape[0]
         bounds = [nf * g // gpus for g in range(gpus + 1)]
         t_block[s] = time.time() - t0
-        texts = {}
-
-        def work(g):
-            lo, hi = bounds[g], bounds[g + 1]
-            if hi <= lo:
-                return
-            with torch.cuda.device(g):
-                res = preds[g].predict_frames(y[lo:hi], u[lo:hi], v[lo:hi], qps=(22, 27, 32, 37))
-                for key, vals in res.items():
-                    from . import ops
-                    texts[(g,) + key] = ops.format_text(vals).cpu().numpy().tobytes()
-
-        t0 = time.time()
-        threads = [threading.Thread(target=work, args=(g,)) for g in range(gpus)]
-        [t.start() for t in threads]
-        [t.join() for t in threads]
-        t_net[s, :, :] = (time.time() - t0) / 8.0
-        t0 = time.time()
+        shards = [g for g in range(gpus) if bounds[g + 1] > bounds[g]]
+        # one worker thread per GPU; .result() re-raises whatever a worker raised (OOM, PmpError, CUDA error): a failed
+        # shard must never turn into a silently truncated PartitionMat file
+        with ThreadPoolExecutor(max_workers=max(1, len(shards))) as pool:
+            futs = {g: pool.submit(_predict_shard, preds[g], y[bounds[g]:bounds[g + 1]], u[bounds[g]:bounds[g + 1]],
+                                   v[bounds[g]:bounds[g + 1]], qps) for g in shards}
+            results = {g: f.result() for g, f in futs.items()}
+        tot = {"blocks": 0, "near_tie_blocks": 0, "near_threshold_blocks": 0, "fp16_saturation_events": 0}
+        for g in shards:
+            for key in tot:
+                tot[key] += results[g][2]["total"][key]
+        print("Decode report: %d block-QPs, %d float32 near-tie argmins, %d with a map value within %g of a decision "
+              "threshold, %d fp16 saturation events" % (tot["blocks"], tot["near_tie_blocks"], tot["near_threshold_blocks"],
+                                                        getattr(args, "nearTol", 1e-2), tot["fp16_saturation_events"]))
+        if tot["fp16_saturation_events"]:
+            raise RuntimeError("activations left the fp16 range (%d events): results are clamped; rerun with --tcDtype bf16"
+                               % tot["fp16_saturation_events"])
         for ci, comp in enumerate(COMPS):
-            for qp in (22, 27, 32, 37):
+            for qi, qp in enumerate(qps):
                 path = PartitionPredictor.partition_path(save_dir, seq_path_name, comp, qp)
                 print("Save:", path)
+                t0 = time.time()
                 with open(path, "wb") as fp:
-                    for g in range(gpus):
-                        fp.write(texts.get((g, comp, qp), b""))
-        t_post[s, :, :] = (time.time() - t0) / 8.0
+                    for g in shards:
+                        fp.write(results[g][0][(comp, qp)])           # KeyError if a shard did not deliver
+                # shards run concurrently: the sequence's time is the slowest GPU's
+                t_net[s, qi, ci] = max(results[g][1][(comp, qp)][0] for g in shards)
+                t_post[s, qi, ci] = max(results[g][1][(comp, qp)][1] for g in shards) + (time.time() - t0)
     log = os.path.join(args.outDir, args.jobID, "Time_Sta_%d_%d.txt" % (args.startSeqID, args.startSeqID + nseq))
     with open(log, "w") as fp:
         for s in range(nseq):
@@ -150,6 +183,8 @@ def inference_VVC_seqs(args):
                 fp.write(",".join(str(x) for x in (t_block[s], t_net[s, q, 0], t_net[s, q, 1], t_post[s, q, 0],
                                                    t_post[s, q, 1])) + ",\n")
     print("Sum time:", np.sum(t_block) + np.sum(t_net) + np.sum(t_post))
+    for p in preds:
+        p.close()
 
 
 def build_parser():
@@ -168,6 +203,9 @@ def build_parser():
     parser.add_argument('--gpus', type=int, default=1)
     parser.add_argument('--engine', type=str, default='tc', choices=['tc', 'simt'])
     parser.add_argument('--missingBD', type=str, default='error', choices=['error', 'seeded'])
+    parser.add_argument('--tcDtype', type=str, default='fp16', choices=['fp16', 'bf16'],
+                        help='16-bit operand format of the split-precision tensor-core engine')
+    parser.add_argument('--nearTol', type=float, default=1e-2, help='tolerance of the near-threshold block count')
     return parser
 
 

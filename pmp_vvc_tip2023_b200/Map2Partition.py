@@ -15,19 +15,20 @@ def _qt_to_u8(qt_map):
     return r.astype(np.uint8)
 
 
-def _decode_batch(qt_map, bt_map, dire_map, chroma_factor, device=None):
+def _decode_batch(qt_map, bt_map, dire_map, chroma_factor, device=None, lamb=None):
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     qt = torch.from_numpy(_qt_to_u8(qt_map).reshape(-1, 64)).to(dev)
     bt = torch.from_numpy(np.ascontiguousarray(bt_map, dtype=np.float32).reshape(-1, 3, 16, 16)).to(dev)
     dire = torch.from_numpy(np.ascontiguousarray(dire_map, dtype=np.float32).reshape(-1, 3, 16, 16)).to(dev)
-    hor, ver, dout, flags = ops.map2partition(qt, bt, dire, chroma_factor)
+    hor, ver, dout, flags = ops.map2partition(qt, bt, dire, chroma_factor, lamb=lamb)
     return qt, hor, ver, dout, flags
 
 
-def map_to_parititon(qt_map, bt_map, dire_map, chroma_factor):
-    """One block: qt [8,8], bt/dire [3,16,16] -> (hor [16,16] u8, ver [16,16] u8, dire [3,16,16] i8)."""
+def map_to_parititon(qt_map, bt_map, dire_map, chroma_factor, lamb=None):
+    """One block: qt [8,8], bt/dire [3,16,16] -> (hor [16,16] u8, ver [16,16] u8, dire [3,16,16] i8).
+    (``lamb``: optional (lamb1..lamb5), an extension -- the reference's wrapper always uses the defaults, :369.)"""
     _, hor, ver, dout, _ = _decode_batch(np.asarray(qt_map)[None], np.asarray(bt_map)[None], np.asarray(dire_map)[None],
-                                         chroma_factor)
+                                         chroma_factor, lamb=lamb)
     return hor[0].cpu().numpy(), ver[0].cpu().numpy(), dout[0].cpu().numpy()
 
 
@@ -36,12 +37,11 @@ class Map_to_Partition:
 
     def __init__(self, qt_map, msbt_map, msdire_map, chroma_factor, lamb1=0.7, lamb2=0.7, lamb3=1.5, lamb4=0.3,
                  lamb5=0.7):
-        if (lamb1, lamb2, lamb3, lamb4, lamb5) != (0.7, 0.7, 1.5, 0.3, 0.7):
-            raise NotImplementedError("the CUDA decode is specialised to the reference's default thresholds")
         self._args = (qt_map, msbt_map, msdire_map, chroma_factor)
+        self.lamb1, self.lamb2, self.lamb3, self.lamb4, self.lamb5 = lamb1, lamb2, lamb3, lamb4, lamb5   # :118-122
 
     def get_partition(self):
-        hor, ver, dout = map_to_parititon(*self._args)
+        hor, ver, dout = map_to_parititon(*self._args, lamb=(self.lamb1, self.lamb2, self.lamb3, self.lamb4, self.lamb5))
         par = np.zeros((2, 17, 17), dtype=np.uint8)
         par[0, :16, :16], par[1, :16, :16] = hor, ver
         return par, dout

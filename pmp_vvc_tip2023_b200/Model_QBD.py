@@ -7,9 +7,11 @@ instead of cuDNN.  Inference only (no autograd); inputs must live on a CUDA devi
 
 The modules hold ordinary ``nn.Conv2d`` children purely as parameter containers so that ``load_state_dict`` with the
 reference ``.pkl`` files, ``nn.DataParallel`` wrapping and ``.cuda()`` behave exactly as with the reference.  Weights
-are packed into the kernels' operand layouts lazily, once per (device, parameter version).
+are packed into the kernels' operand layouts lazily, once per (device, parameter version), in a small LRU per
+(device, net kind) so that alternating QPs / DataParallel replicas do not re-pack on every forward.
 """
 import ctypes
+from collections import OrderedDict
 
 import torch
 import torch.nn as nn
@@ -43,19 +45,37 @@ def _make_layer(cin, couts, ks):
     return nn.Sequential(*layers)
 
 
+_WSET_LRU = 8            # packed weight sets kept per (device, net kind): 4 QPs x (module, DataParallel replica)
+_WSET_CACHE = {}         # (device, net kind) -> OrderedDict{fingerprint: wset id}
+
+
 class _PmpNet(nn.Module):
     """Shared plumbing: weight-set cache and the C-ABI call."""
     NET = None
 
     def __init__(self):
         super().__init__()
-        self._wsets = {}         # device index -> (fingerprint, wset id)
+        self._wgen = 0           # bumped by load_state_dict / invalidate_weights(): part of the cache fingerprint
+        self._src_fp = None      # set on nn.DataParallel replicas: fingerprint of the module they were replicated from
 
-    # the cache must not leak into replicas/pickles with stale ids
-    def __getstate__(self):
-        st = self.__dict__.copy()
-        st["_wsets"] = {}
-        return st
+    def invalidate_weights(self):
+        """Force a re-pack of the kernels' operand images on the next forward.  ``load_state_dict`` does this by itself;
+        call it after in-place updates through ``param.data`` (those do not bump the parameter's version counter)."""
+        self._wgen += 1
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._wgen += 1
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _fingerprint(self):
+        return (id(self), self._wgen) + tuple((p.data_ptr(), p._version) for p in self._param_list())
+
+    def _replicate_for_data_parallel(self):
+        # runs on the SOURCE module once per replica (torch/nn/parallel/replicate.py): the replica's broadcast weight
+        # copies are new tensors every forward, so they are identified by the source's fingerprint (no device sync)
+        replica = super()._replicate_for_data_parallel()
+        replica._src_fp = self._fingerprint()
+        return replica
 
     def _param_list(self):
         # attribute walk, not named_parameters(): nn.DataParallel replicas on the other GPUs carry their weights as plain
@@ -69,22 +89,15 @@ class _PmpNet(nn.Module):
         return out
 
     def _weight_set(self, device):
-        params = self._param_list()
-        if getattr(self, "_is_replica", False):
-            # DataParallel replicas are rebuilt every forward: identify the weights by content
-            with torch.no_grad():
-                flat = torch.cat([p.reshape(-1) for p in params]).double()
-                fp = ("replica", float(flat.sum()), float((flat * flat).sum()))
-            cache = _REPLICA_CACHE.setdefault((device, self.NET), {})
-        else:
-            fp = tuple((p.data_ptr(), p._version) for p in params)
-            cache = self._wsets.setdefault(device, {})
-        if fp not in cache:
-            h = _lib.Handle.get(device)
-            for old in list(cache.values()):
-                h.weights_destroy(old)
-            cache.clear()
-            cache[fp] = h.weights_create(self.NET, [p.detach() for p in params])
+        fp = self._src_fp if getattr(self, "_is_replica", False) and self._src_fp is not None else self._fingerprint()
+        cache = _WSET_CACHE.setdefault((device, self.NET), OrderedDict())
+        if fp in cache:
+            cache.move_to_end(fp)
+            return cache[fp]
+        h = _lib.Handle.get(device)
+        while len(cache) >= _WSET_LRU:
+            h.weights_destroy(cache.popitem(last=False)[1])
+        cache[fp] = h.weights_create(self.NET, [p.detach() for p in self._param_list()])
         return cache[fp]
 
     @staticmethod
@@ -97,9 +110,6 @@ class _PmpNet(nn.Module):
         if x.dtype == torch.uint8:
             return x.contiguous(), _lib.IN_U8
         return x.contiguous().float(), _lib.IN_F32
-
-
-_REPLICA_CACHE = {}
 
 
 def _stream(device):

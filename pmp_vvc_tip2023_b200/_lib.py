@@ -24,6 +24,8 @@ SIGNATURES = {
     "pmp_destroy": (None, [c_void_p]),
     "pmp_set_engine": (c_int, [c_void_p, c_int, c_int]),
     "pmp_get_engine": (c_int, [c_void_p]),
+    "pmp_set_near_tol": (c_int, [c_void_p, ctypes.c_float]),
+    "pmp_saturation_count": (c_int, [c_void_p, _P(ctypes.c_longlong), c_int]),
     "pmp_launch_count": (ctypes.c_longlong, [c_void_p]),
     "pmp_profile": (c_int, [c_void_p, c_int]),
     "pmp_profile_read": (c_int, [c_void_p, c_int, c_char_p, c_int, _P(ctypes.c_double), _P(ctypes.c_longlong),
@@ -38,6 +40,8 @@ SIGNATURES = {
     "pmp_qt_postprocess": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "pmp_map2partition": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
+    "pmp_map2partition_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, _P(ctypes.c_double), c_void_p,
+                                     ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pmp_assemble_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                     c_void_p]),
     "pmp_frame_values": (c_int64, [c_int, c_int]),
@@ -48,6 +52,9 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pmp_selftest_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, _P(ctypes.c_double),
                                   _P(ctypes.c_double), _P(ctypes.c_double), _P(ctypes.c_double)]),
+    "pmp_debug_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                               c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pmp_debug_stem": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "pmp_debug_tc_stalls": (c_int, [_P(ctypes.c_uint64), c_int]),
 }
 
@@ -83,7 +90,9 @@ def check(rc):
 
 
 class Handle:
-    """One pmp_handle per (process, device).  Not thread-safe; one stream at a time."""
+    """A pmp_handle (engine selection, weight sets, activation arena).  ``Handle.get(device)`` is the per-(process, device)
+    default used by the Model_QBD modules and the module-level ops; a PartitionPredictor owns a private one, so that its
+    engine choice and arena are its own.  Not thread-safe; one stream at a time per handle."""
     _cache = {}
 
     def __init__(self, device=0):
@@ -107,7 +116,8 @@ class Handle:
         if self._h:
             lib().pmp_destroy(self._h)
             self._h = c_void_p()
-        Handle._cache.pop(self.device, None)
+        if Handle._cache.get(self.device) is self:
+            Handle._cache.pop(self.device, None)
 
     # ---- engine / counters ------------------------------------------------------------------
     def set_engine(self, engine, tc_dtype=TC_FP16):
@@ -115,6 +125,15 @@ class Handle:
 
     def engine(self):
         return lib().pmp_get_engine(self._h)
+
+    def set_near_tol(self, tol):
+        check(lib().pmp_set_near_tol(self._h, float(tol)))
+
+    def saturation_count(self, reset=False):
+        """fp16 range-guard events of the TC conv epilogues (non-zero => results clamped: use tc_dtype='bf16')."""
+        n = ctypes.c_longlong()
+        check(lib().pmp_saturation_count(self._h, ctypes.byref(n), 1 if reset else 0))
+        return int(n.value)
 
     def launch_count(self):
         return int(lib().pmp_launch_count(self._h))

@@ -98,6 +98,14 @@ int ensure_scratch(Handle *h, size_t bytes)
     return PMP_OK;
 }
 
+int ensure_status(Handle *h)
+{
+    if (h->d_status) return PMP_OK;
+    PMP_CUDA(cudaMalloc((void **)&h->d_status, 64));
+    PMP_CUDA(cudaMemset(h->d_status, 0, 64));
+    return PMP_OK;
+}
+
 }  // namespace pmp
 
 using namespace pmp;
@@ -155,6 +163,7 @@ void pmp_destroy(pmp_handle *h)
     for (int id : ids) weights_destroy(h, id);
     if (h->arena) cudaFree(h->arena);
     if (h->scratch) cudaFree(h->scratch);
+    if (h->d_status) cudaFree(h->d_status);
     delete h;
 }
 
@@ -169,6 +178,28 @@ int pmp_set_engine(pmp_handle *h, int engine, int tc_dtype)
 }
 
 int pmp_get_engine(pmp_handle *h) { return h ? h->engine : PMP_ERR_ARG; }
+
+int pmp_set_near_tol(pmp_handle *h, float near_tol)
+{
+    H_CHECK(h);
+    PMP_CHECK_ARG(near_tol >= 0.f && near_tol <= 0.5f, "near_tol must be in [0, 0.5]");
+    h->near_tol = near_tol;
+    return PMP_OK;
+}
+
+int pmp_saturation_count(pmp_handle *h, long long *count_host, int reset)
+{
+    H_CHECK(h);
+    PMP_CHECK_ARG(count_host != nullptr, "null pointer");
+    *count_host = 0;
+    if (!h->d_status) return PMP_OK;
+    unsigned int v = 0;
+    PMP_CUDA(cudaDeviceSynchronize());
+    PMP_CUDA(cudaMemcpy(&v, h->d_status, sizeof(v), cudaMemcpyDeviceToHost));
+    if (reset) PMP_CUDA(cudaMemset(h->d_status, 0, sizeof(v)));
+    *count_host = (long long)v;
+    return PMP_OK;
+}
 
 long long pmp_launch_count(pmp_handle *h) { return h ? h->launches : -1; }
 
@@ -252,6 +283,15 @@ int pmp_predict_maps(pmp_handle *h, int wset_q, int wset_msbd, const void *block
                         s);
 }
 
+int pmp_debug_stem(pmp_handle *h, int wset, const void *blocks, int in_dtype, const float *qt, int B, float *out,
+                   void *stream)
+{
+    H_CHECK(h);
+    PMP_CHECK_ARG(B > 0 && blocks && out, "bad argument");
+    PMP_CHECK_ARG(in_dtype == PMP_IN_U8 || in_dtype == PMP_IN_F32, "unknown input dtype");
+    return debug_stem(h, wset, blocks, in_dtype, qt, B, out, (cudaStream_t)stream);
+}
+
 int pmp_qt_postprocess(pmp_handle *h, const float *qt, int B, float *out_f32, uint8_t *out_u8, void *stream)
 {
     H_CHECK(h);
@@ -268,7 +308,21 @@ int pmp_map2partition(pmp_handle *h, const uint8_t *qt_u8, const float *bt, cons
     PMP_CHECK_ARG(B >= 0, "negative batch");
     if (B == 0) return PMP_OK;
     PMP_CHECK_ARG(qt_u8 && bt && dire && hor && ver && dire_out, "null pointer");
-    return map2partition(h, qt_u8, bt, dire, B, chroma_factor, hor, ver, dire_out, flags, (cudaStream_t)stream);
+    return map2partition(h, qt_u8, bt, dire, B, chroma_factor, hor, ver, dire_out, flags, (cudaStream_t)stream, nullptr,
+                         nullptr, h->near_tol);
+}
+
+int pmp_map2partition_ex(pmp_handle *h, const uint8_t *qt_u8, const float *bt, const float *dire, int B, int chroma_factor,
+                         const double *lamb, const float *qt_raw, float near_tol, uint8_t *hor, uint8_t *ver,
+                         int8_t *dire_out, uint32_t *flags, void *stream)
+{
+    H_CHECK(h);
+    PMP_CHECK_ARG(B >= 0, "negative batch");
+    if (B == 0) return PMP_OK;
+    PMP_CHECK_ARG(qt_u8 && bt && dire && hor && ver && dire_out, "null pointer");
+    PMP_CHECK_ARG(near_tol >= 0.f && near_tol <= 0.5f, "near_tol must be in [0, 0.5]");
+    return map2partition(h, qt_u8, bt, dire, B, chroma_factor, hor, ver, dire_out, flags, (cudaStream_t)stream, lamb, qt_raw,
+                         near_tol);
 }
 
 int pmp_assemble_frames(pmp_handle *h, const uint8_t *hor, const uint8_t *ver, const uint8_t *qt_u8, const int8_t *dire,
@@ -332,7 +386,7 @@ int pmp_run_component(pmp_handle *h, int wset_q, int wset_msbd, int luma, const 
         rc = qt_postprocess(h, pqt, nb, nullptr, qt8 + b0 * 64, s);
         if (rc) return rc;
         rc = map2partition(h, qt8 + b0 * 64, pbt, pdi, nb, luma ? 1 : 2, hor + b0 * 256, ver + b0 * 256, dout + b0 * 768,
-                           flags ? flags + b0 : nullptr, s);
+                           flags ? flags + b0 : nullptr, s, nullptr, pqt, h->near_tol);
         if (rc) return rc;
     }
     return assemble_frames(h, hor, ver, qt8, dout, frames, bh, bw, out, s);

@@ -364,6 +364,8 @@ struct TcParams {
     uint32_t pair_slab;     // CTA-pair kernel: bytes of one per-CTA weight slab
     int pair_split;         // CTA-pair kernel: rows of the weight tensor map per slab (1, or 2 for 3 KB slabs)
     int kws;                // CTA-pair kernel: taps per ring stage (kw = one filter row, or 1 when rows do not fit)
+    unsigned int *sat;      // handle status word 0: count of epilogue threads that produced |value| > 65504 with fp16 operands
+                            // (the hi/lo split clamps there: results beyond are wrong) -- sticky, read by pmp_saturation_count
 };
 
 struct TileGeom { int n, mt_count, q0, row0, qoff; };
@@ -428,6 +430,18 @@ __device__ __forceinline__ void unpack_split(const uint4 &H, const uint4 &L, boo
     }
 }
 
+// fp16 range guard of the hi/lo split (split2 clamps to +-65504): report instead of clamping silently
+template <int CH>
+__device__ __forceinline__ void saturation_check(const TcParams &p, const float (&v)[CH][8])
+{
+    float am = 0.f;
+#pragma unroll
+    for (int j = 0; j < CH; j++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) am = fmaxf(am, fabsf(v[j][e]));
+    if (am > 65504.f && !p.out.bf16 && p.sat) atomicAdd(p.sat, 1u);
+}
+
 // Epilogue of one M-tile for CH consecutive 8-channel chunks starting at chunk ch0 (one thread = one position).
 template <int CH>
 __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t taddr, int ch0, int n, int r, int c, bool valid)
@@ -486,6 +500,7 @@ __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t tadd
 #pragma unroll
             for (int e = 0; e < 8; e++) v[j][e] = fmaxf(v[j][e], __shfl_xor_sync(0xffffffffu, v[j][e], 1));
         if (!valid || (c & 1)) return;
+        saturation_check<CH>(p, v);
         const bool bfh = p.out.bf16 != 0;
         const size_t hplane = (size_t)p.H * (p.W >> 1);
         uint4 *obh = reinterpret_cast<uint4 *>(p.out.p) + (size_t)n * (p.out.Cp >> 2) * hplane + (size_t)r * (p.W >> 1) + (c >> 1);
@@ -548,6 +563,7 @@ __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t tadd
         q[0] = Hh;
         q[2 * plane] = Ll;
     }
+    saturation_check<CH>(p, v);
 }
 
 // Persistent, warp-specialised: warp 0 weight producer, warp 1 activation producer + TMEM owner, warps 2..5 MMA issuers
@@ -1254,6 +1270,8 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     }
     static const int env_dbg = [] { const char *e = getenv("PMP_TC_DBG"); return e ? atoi(e) : 0; }();   // bit 6: per-role stall counters
     p.dbg = env_dbg;
+    { int rcs = ensure_status(h); if (rcs) return rcs; }
+    p.sat = h->d_status;
     if (!h->tc_attr_set) {          // function attributes are per device: one handle per device
         PMP_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
         PMP_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
@@ -1261,6 +1279,11 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
     }
     const double flops = a.flops_override > 0 ? a.flops_override * B
                                                : 2.0 * B * H * W * (double)a.out.C * ((double)a.in.C * a.kh * a.kw + (a.sc_in.p ? a.sc_in.C : 0));
+    // algorithmic HBM bytes of the launch: every operand tensor once at 4 B/element (hi + lo), weights excluded (L2-resident)
+    const double hbm_bytes = (stem ? (double)B * a.stem_planes * a.stem_rows * a.stem_uw * 128.0
+                                   : (double)B * a.cin_pad * Hin * W * 4.0) +
+                             (double)B * a.cout_pad * H * (a.hpool ? W / 2 : W) * 4.0 * (1.0 + (a.res.p ? 1.0 : 0.0) + (a.mul.p ? 1.0 : 0.0)) +
+                             (a.sc_in.p ? (double)B * a.sc_cin_pad * Hin * W * 4.0 : 0.0);
     if (a.sc_in.p && (!use_pair || !a.w_pair_sc || a.sc_in.fmt != FMT_SPLIT || a.sc_in.H != Hin || a.sc_in.W != W ||
                       a.sc_in.Cp != a.sc_cin_pad || a.sc_cin_pad % 16 || a.res.p)) {
         set_error("conv_tc: fused shortcut needs the CTA-pair kernel, a split-format second input of the same size and no residual");
@@ -1342,7 +1365,7 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         p.idesc2 = idesc_base_nom | ((uint32_t)(g.N1 >> 3) << 17) | ((256u >> 4) << 24);         // stacked: N = 2*Cout
         int nsm = h->num_sms & ~1;
         int grid = 2 * p.pair_items < nsm ? 2 * p.pair_items : nsm;
-        ProfScope ps(h, PROF_CONV_TC, s, flops, 0);
+        ProfScope ps(h, PROF_CONV_TC, s, flops, hbm_bytes);
         static const int env_pdl = [] { const char *e = getenv("PMP_TC_PDL"); return e ? atoi(e) : 1; }();
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem_pair; cfg.stream = s;
@@ -1355,7 +1378,7 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         return PMP_OK;
     }
     dim3 grid(p.items < h->num_sms ? p.items : h->num_sms);
-    ProfScope ps(h, PROF_CONV_TC, s, flops, 0);
+    ProfScope ps(h, PROF_CONV_TC, s, flops, hbm_bytes);
     conv_tc_kernel<<<grid, TC_THREADS, g.smem_bytes, s>>>(tmap, p);
     h->launches++;
     PMP_CUDA(cudaGetLastError());
@@ -1528,6 +1551,15 @@ __global__ void split_to_f32_kernel(Act src, float *__restrict__ dst, int B)
         int n = (int)(i / ((size_t)src.W * src.H * src.C));
         dst[i] = load_elem(src, n, c, y, x);
     }
+}
+
+int split_to_f32(Handle *h, const Act &src, float *dst, int B, cudaStream_t s)
+{
+    if (B <= 0) return PMP_OK;
+    split_to_f32_kernel<<<1024, 256, 0, s>>>(src, dst, B);
+    h->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
 }
 
 }  // namespace pmp
@@ -1775,5 +1807,82 @@ extern "C" int pmp_selftest_conv(pmp_handle *h, int cin, int cout, int ksize, in
     if (ref_absmax) *ref_absmax = am;
     if (ms_tc) *ms_tc = t_tc;
     if (ms_simt) *ms_simt = t_simt;
+    return PMP_OK;
+}
+
+
+// Test hook: one TC-engine convolution on caller-supplied fp32 data (device pointers: NCHW activations; HOST pointers:
+// weights in the reference's [cout][cin][k][k] / [cout][cin2] layout), so that tests can compare the tcgen05 kernels with
+// an independent convolution (torch F.conv2d on the CPU) instead of this library's own SIMT conv.
+// flags: bit0 ReLU, bit3 bf16 operands, bit18 2x2 max-pool (horizontal half fused into the epilogue + pool2_split);
+// res / mul: identity residual / attention product operands ([B,cout,H,W], mul at the stored output's size) or NULL;
+// in2 + w_sc_host: fused 1x1 shortcut on a second input with cin2 channels, or NULL.  out: [B,cout,Ho,Wo] fp32.
+extern "C" int pmp_debug_conv(pmp_handle *h, const float *in, const float *w_host, const float *res, const float *mul,
+                              const float *in2, const float *w_sc_host, int cin, int cout, int ksize, int hw, int batch,
+                              int cin2, int flags, float *out, void *stream)
+{
+    if (!h || !in || !w_host || !out) { set_error("pmp_debug_conv: null pointer"); return PMP_ERR_ARG; }
+    PMP_CUDA(cudaSetDevice(h->device));
+    const int B = batch, H = hw, W = hw;
+    const bool bf = (flags & 8) != 0, pooled = (flags >> 18) & 1, fused = in2 != nullptr;
+    const int cinp = pad16(cin), coutp = pad16(cout), cin2p = pad16(cin2);
+    if (B <= 0 || !tc_supported(cinp, coutp, ksize, ksize, H, W) || (fused && (!w_sc_host || cin2 <= 0 || res)) ||
+        (pooled && (mul || (W & 1) || (H & 1)))) {
+        set_error("pmp_debug_conv: configuration not supported by the TC engine");
+        return PMP_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    DevBuf d_in, d_res, d_mul, d_in2, d_out, d_tmp, d_wtc, d_wpair, d_wsc;
+    const size_t sp_in = act_bytes(FMT_SPLIT, B, cin, H, W), sp_out = act_bytes(FMT_SPLIT, B, cout, H, W);
+    std::vector<uint16_t> pk(tc_packed_elems(cinp, coutp, ksize, ksize)), pp(tc_pair_packed_elems(cinp, coutp, ksize, ksize));
+    pack_tc_weights(w_host, cout, cin, ksize, ksize, cinp, coutp, bf, pk.data());
+    pack_tc_pair_weights(w_host, cout, cin, ksize, ksize, cinp, coutp, bf, pp.data());
+    if (d_in.alloc(sp_in) || d_out.alloc(sp_out) || d_tmp.alloc(sp_out) || d_wtc.alloc(pk.size() * 2) || d_wpair.alloc(pp.size() * 2) ||
+        (res && d_res.alloc(sp_out)) || (mul && d_mul.alloc(sp_out)) || (fused && d_in2.alloc(act_bytes(FMT_SPLIT, B, cin2, H, W)))) {
+        set_error("pmp_debug_conv: cudaMalloc failed");
+        return PMP_ERR_CUDA;
+    }
+    PMP_CUDA(cudaMemcpyAsync(d_wtc.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice, s));
+    PMP_CUDA(cudaMemcpyAsync(d_wpair.p, pp.data(), pp.size() * 2, cudaMemcpyHostToDevice, s));
+    std::vector<uint16_t> pf;
+    if (fused) {
+        pf.resize(tc_pair_fused_sc_elems(cin2p, coutp, ksize, ksize));
+        pack_tc_pair_fused_sc(w_sc_host, cout, cin2, cin2p, coutp, ksize, ksize, bf, pf.data());
+        if (d_wsc.alloc(pf.size() * 2)) { set_error("pmp_debug_conv: cudaMalloc failed"); return PMP_ERR_CUDA; }
+        PMP_CUDA(cudaMemcpyAsync(d_wsc.p, pf.data(), pf.size() * 2, cudaMemcpyHostToDevice, s));
+    }
+    auto mk = [&](void *p, int C, int hh, int ww) {
+        Act a;
+        a.p = p; a.fmt = FMT_SPLIT; a.C = C; a.Cp = pad16(C); a.H = hh; a.W = ww; a.bf16 = bf;
+        return a;
+    };
+    const int Ho = pooled ? H / 2 : H, Wo = pooled ? W / 2 : W;
+    Act a_in = mk(d_in.p, cin, H, W), a_out = mk(d_out.p, cout, H, pooled ? W / 2 : W);
+    f32_to_split_kernel<<<1024, 256, 0, s>>>(in, a_in, B);
+    TcConvArgs ta;
+    ta.in = a_in; ta.out = a_out;
+    if (res) { ta.res = mk(d_res.p, cout, H, W); f32_to_split_kernel<<<1024, 256, 0, s>>>(res, ta.res, B); }
+    Act a_mul;
+    if (mul) { a_mul = mk(d_mul.p, cout, Ho, Wo); f32_to_split_kernel<<<1024, 256, 0, s>>>(mul, a_mul, B); }
+    if (mul && !pooled) ta.mul = a_mul;
+    if (fused) {
+        ta.sc_in = mk(d_in2.p, cin2, H, W);
+        f32_to_split_kernel<<<1024, 256, 0, s>>>(in2, ta.sc_in, B);
+        ta.w_pair_sc = (const uint16_t *)d_wsc.p; ta.sc_cin_pad = cin2p;
+    }
+    ta.w = (const uint16_t *)d_wtc.p; ta.w_pair = (const uint16_t *)d_wpair.p;
+    ta.cin_pad = cinp; ta.cout_pad = coutp; ta.kh = ta.kw = ksize; ta.pad_t = ta.pad_l = ksize / 2; ta.relu = flags & 1; ta.pool = 1;
+    ta.hpool = pooled ? 1 : 0;
+    int rc = conv_tc(h, ta, B, s);
+    if (rc) return rc;
+    Act fin = a_out;
+    if (pooled) {
+        fin = mk(d_tmp.p, cout, Ho, Wo);
+        rc = pool2_split(h, a_out, fin, Act(), B, s);
+        if (rc) return rc;
+    }
+    split_to_f32_kernel<<<1024, 256, 0, s>>>(fin, out, B);
+    PMP_CUDA(cudaGetLastError());
+    PMP_CUDA(cudaStreamSynchronize(s));      // the temporaries are freed on return
     return PMP_OK;
 }

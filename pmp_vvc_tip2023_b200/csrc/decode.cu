@@ -27,69 +27,84 @@ namespace pmp {
 // ------------------------------------------------------------------------------------------
 // D1/D2: QT-map post-process, one thread per block
 // ------------------------------------------------------------------------------------------
-__global__ void qt_postprocess_kernel(const float *__restrict__ qt, int B, float *__restrict__ out_f32,
-                                      uint8_t *__restrict__ out_u8)
+constexpr int QT_TPB = 128;
+
+// One thread per block for the 4x4 integer rules; loads and stores go through shared memory so that global accesses
+// are coalesced (a block's 64 floats are 256 contiguous bytes; thread-per-block strided accesses wasted 7/8 of every sector).
+__global__ void __launch_bounds__(QT_TPB)
+qt_postprocess_kernel(const float *__restrict__ qt, int B, float *__restrict__ out_f32, uint8_t *__restrict__ out_u8)
 {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const float *q = qt + (size_t)b * 64;
-    int m[16];
-    int n0 = 0;
+    __shared__ float sq[QT_TPB * 65];            // row pitch 65: conflict-free scalar reads by the owning thread
+    __shared__ uint32_t sm4[QT_TPB * 4];         // repaired 4x4 map, 16 bytes per block
+    const int b0 = blockIdx.x * QT_TPB;
+    const int nb = (B - b0) < QT_TPB ? (B - b0) : QT_TPB;
+    for (int k = threadIdx.x; k < nb * 64; k += QT_TPB) sq[(k >> 6) * 65 + (k & 63)] = qt[(size_t)b0 * 64 + k];
+    __syncthreads();
+    if ((int)threadIdx.x < nb) {
+        const float *q = sq + threadIdx.x * 65;
+        int m[16];
+        int n0 = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+        for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float2 r0 = *reinterpret_cast<const float2 *>(q + (2 * i) * 8 + 2 * j);
-            float2 r1 = *reinterpret_cast<const float2 *>(q + (2 * i + 1) * 8 + 2 * j);
-            float mx = fmaxf(fmaxf(r0.x, r0.y), fmaxf(r1.x, r1.y));      // max_pool2d(.,2)
-            float r = rintf(mx);                                         // torch.round: half to even
-            r = fminf(fmaxf(r, 0.f), 3.f);                               // clamp [0,3]
-            int v = (int)r;
-            m[i * 4 + j] = v;
-            n0 += (v == 0);
-        }
-    if (n0 <= 12) {
-#pragma unroll
-        for (int k = 0; k < 16; k++)
-            if (m[k] == 0) m[k] = 1;
-#pragma unroll
-        for (int i = 0; i < 4; i += 2)
-#pragma unroll
-            for (int j = 0; j < 4; j += 2) {
-                int a = m[i * 4 + j], bq = m[i * 4 + j + 1], c = m[(i + 1) * 4 + j], d = m[(i + 1) * 4 + j + 1];
-                int s = a + bq + c + d;
-                if (s >= 5 && s <= 10) {
-                    int n1 = (a == 1) + (bq == 1) + (c == 1) + (d == 1);
-                    if (n1 < 3) {
-                        if (a == 1) a = 2;
-                        if (bq == 1) bq = 2;
-                        if (c == 1) c = 2;
-                        if (d == 1) d = 2;
-                    } else {
-                        a = bq = c = d = 1;
-                    }
-                    m[i * 4 + j] = a; m[i * 4 + j + 1] = bq; m[(i + 1) * 4 + j] = c; m[(i + 1) * 4 + j + 1] = d;
-                }
+            for (int j = 0; j < 4; j++) {
+                const float *r0 = q + (2 * i) * 8 + 2 * j, *r1 = r0 + 8;
+                float mx = fmaxf(fmaxf(r0[0], r0[1]), fmaxf(r1[0], r1[1]));  // max_pool2d(.,2)
+                float r = rintf(mx);                                         // torch.round: half to even
+                r = fminf(fmaxf(r, 0.f), 3.f);                               // clamp [0,3]
+                int v = (int)r;
+                m[i * 4 + j] = v;
+                n0 += (v == 0);
             }
-    } else if (n0 < 16) {
+        if (n0 <= 12) {
 #pragma unroll
-        for (int k = 0; k < 16; k++) m[k] = 0;
-    }
+            for (int k = 0; k < 16; k++)
+                if (m[k] == 0) m[k] = 1;
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+            for (int i = 0; i < 4; i += 2)
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            int v = m[(i >> 1) * 4 + (j >> 1)];                           // nearest x2
-            if (out_f32) out_f32[(size_t)b * 64 + i * 8 + j] = (float)v;
-            if (out_u8) out_u8[(size_t)b * 64 + i * 8 + j] = (uint8_t)v;
+                for (int j = 0; j < 4; j += 2) {
+                    int a = m[i * 4 + j], bq = m[i * 4 + j + 1], c = m[(i + 1) * 4 + j], d = m[(i + 1) * 4 + j + 1];
+                    int s = a + bq + c + d;
+                    if (s >= 5 && s <= 10) {
+                        int n1 = (a == 1) + (bq == 1) + (c == 1) + (d == 1);
+                        if (n1 < 3) {
+                            if (a == 1) a = 2;
+                            if (bq == 1) bq = 2;
+                            if (c == 1) c = 2;
+                            if (d == 1) d = 2;
+                        } else {
+                            a = bq = c = d = 1;
+                        }
+                        m[i * 4 + j] = a; m[i * 4 + j + 1] = bq; m[(i + 1) * 4 + j] = c; m[(i + 1) * 4 + j + 1] = d;
+                    }
+                }
+        } else if (n0 < 16) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) m[k] = 0;
         }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            sm4[threadIdx.x * 4 + i] = (uint32_t)m[i * 4] | ((uint32_t)m[i * 4 + 1] << 8) | ((uint32_t)m[i * 4 + 2] << 16) |
+                                       ((uint32_t)m[i * 4 + 3] << 24);
+    }
+    __syncthreads();
+    // nearest x2 while writing: word k4 of the tile = output row i, column half jh of block bb
+    for (int k4 = threadIdx.x; k4 < nb * 16; k4 += QT_TPB) {
+        const int bb = k4 >> 4, i = (k4 >> 1) & 7, jh = k4 & 1;
+        const uint32_t row = sm4[bb * 4 + (i >> 1)] >> (16 * jh);
+        const uint32_t v0 = row & 0xffu, v1 = (row >> 8) & 0xffu;
+        if (out_u8) reinterpret_cast<uint32_t *>(out_u8)[(size_t)b0 * 16 + k4] = v0 | (v0 << 8) | (v1 << 16) | (v1 << 24);
+        if (out_f32) reinterpret_cast<float4 *>(out_f32)[(size_t)b0 * 16 + k4] = make_float4((float)v0, (float)v0, (float)v1, (float)v1);
+    }
 }
 
 int qt_postprocess(Handle *h, const float *qt, int B, float *out_f32, uint8_t *out_u8, cudaStream_t s)
 {
     if (B <= 0) return PMP_OK;
+    PMP_CHECK_ARG((((uintptr_t)out_u8) & 3) == 0 && (((uintptr_t)out_f32) & 15) == 0, "qt_postprocess outputs must be 4/16-byte aligned");
     ProfScope ps(h, PROF_POSTPROC, s, 0, (double)B * (256 + 64 + (out_f32 ? 256 : 0)));
-    qt_postprocess_kernel<<<cdiv(B, 128), 128, 0, s>>>(qt, B, out_f32, out_u8);
+    qt_postprocess_kernel<<<cdiv(B, QT_TPB), QT_TPB, 0, s>>>(qt, B, out_f32, out_u8);
     h->launches++;
     PMP_CUDA(cudaGetLastError());
     return PMP_OK;
@@ -149,8 +164,11 @@ __device__ __forceinline__ int sub_of(int off, int len, bool tt)
     return off < (len >> 2) ? 0 : (off < ((len * 3) >> 2) ? 1 : 2);
 }
 
+// Decode thresholds lamb1..lamb5 (Map2Partition.py:100,:118-122; Python floats, i.e. doubles) -- kernel parameters.
+struct Lamb { double l1, l2, l3, l4, l5; };
+
 // Map2Partition.py:140-201 (candidate list) + the level-d error terms of :307-312 for one CU.
-__device__ Eval eval_cu(const WarpMaps &wm, int lane, int x, int y, int h, int w, int d, int cur, int cf)
+__device__ Eval eval_cu(const WarpMaps &wm, const Lamb &lb, int lane, int x, int y, int h, int w, int d, int cur, int cf)
 {
     const int n = h * w;
     // legality (:158-165); horizontal modes split h, vertical modes split w
@@ -207,13 +225,13 @@ __device__ Eval eval_cu(const WarpMaps &wm, int lane, int x, int y, int h, int w
     ev.cand = 1u;
     int zero2 = misc & 1023, nh = (misc >> 10) & 1023, nv = (misc >> 20) & 1023;
     // (i) already at final depth on >= 70% of the CU: no split (:142-145).  Products are formed in
-    // double in the reference's association order: (0.7*h)*w.
-    if ((double)zero2 >= 0.7 * (double)h * (double)w) return ev;
+    // double in the reference's association order: (lamb1*h)*w.
+    if ((double)zero2 >= lb.l1 * (double)h * (double)w) return ev;
     // (ii) direction vote (:146-154)
     int direction = 0;
-    if ((double)(nv + nh) >= 0.7 * (double)h * (double)w) {
-        if ((double)nh >= 1.5 * (double)nv) direction = 1;
-        else if ((double)nv >= 1.5 * (double)nh) direction = 2;
+    if ((double)(nv + nh) >= lb.l2 * (double)h * (double)w) {
+        if ((double)nh >= lb.l3 * (double)nv) direction = 1;
+        else if ((double)nv >= lb.l3 * (double)nh) direction = 2;
     }
 #pragma unroll
     for (int m = 1; m <= 4; m++) {
@@ -227,7 +245,7 @@ __device__ Eval eval_cu(const WarpMaps &wm, int lane, int x, int y, int h, int w
             int len = (m & 1) ? h : w, oth = (m & 1) ? w : h;
             int sl = (m >= 3) ? ((s == 1) ? (len >> 1) : (len >> 2)) : (len >> 1);
             int np = sl * oth;
-            if (!((double)minus < (double)np * 0.3 && (double)zero > (double)np * 0.7)) ok = false;   // (:194)
+            if (!((double)minus < (double)np * lb.l4 && (double)zero > (double)np * lb.l5)) ok = false;   // (:194)
         }
         if (ok) ev.cand |= 1u << m;
     }
@@ -250,9 +268,9 @@ template <> struct ModeBits<2> { static constexpr int value = 3; };
 constexpr i64 GAP_INF = (i64)1 << 62;
 
 template <int D>
-__device__ Cost best_cu(const WarpMaps &wm, int lane, int x, int y, int h, int w, int cur, int cf)
+__device__ Cost best_cu(const WarpMaps &wm, const Lamb &lb, int lane, int x, int y, int h, int w, int cur, int cf)
 {
-    Eval ev = eval_cu(wm, lane, x, y, h, w, D, cur, cf);
+    Eval ev = eval_cu(wm, lb, lane, x, y, h, w, D, cur, cf);
     Cost best;
     best.e5 = GAP_INF; best.sd = 0; best.mingap = GAP_INF; best.modes = 0;
     i64 second_e5 = GAP_INF, second_sd = 0;
@@ -268,7 +286,7 @@ __device__ Cost best_cu(const WarpMaps &wm, int lane, int x, int y, int h, int w
                 int cx, cy, ch, cw;
                 child_rect(x, y, h, w, m, c, cx, cy, ch, cw);
                 int v = cur + ((m == 0) ? 0 : ((m >= 3 && c != 1) ? 2 : 1));
-                Cost cr = best_cu<D + 1>(wm, lane, cx, cy, ch, cw, v, cf);
+                Cost cr = best_cu<D + 1>(wm, lb, lane, cx, cy, ch, cw, v, cf);
                 r.e5 += cr.e5; r.sd += cr.sd;
                 r.mingap = cr.mingap < r.mingap ? cr.mingap : r.mingap;
                 r.modes |= cr.modes << (3 + c * ModeBits<D + 1>::value);
@@ -318,8 +336,9 @@ __device__ void apply_tree(WarpMaps &wm, int lane, int x, int y, int h, int w, u
 
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 map2partition_kernel(const uint8_t *__restrict__ qt, const float *__restrict__ bt, const float *__restrict__ dire,
-                     int B, int cf, uint8_t *__restrict__ hor, uint8_t *__restrict__ ver,
-                     int8_t *__restrict__ dout, uint32_t *__restrict__ flags)
+                     int B, int cf, const Lamb lb, const float *__restrict__ qt_raw, float near_tol,
+                     uint8_t *__restrict__ hor, uint8_t *__restrict__ ver, int8_t *__restrict__ dout,
+                     uint32_t *__restrict__ flags)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -329,6 +348,11 @@ map2partition_kernel(const uint8_t *__restrict__ qt, const float *__restrict__ b
         // ---- stage: coalesced float4 loads, threshold maps (D3: :104-105) ----
         const float4 *bt4 = reinterpret_cast<const float4 *>(bt + (size_t)b * 768);
         const float4 *di4 = reinterpret_cast<const float4 *>(dire + (size_t)b * 768);
+        // near-threshold report (north star: "a reported count of CTUs whose values fall within tolerance of a decision
+        // threshold"): bit1 a depth value within near_tol of a rounding threshold k + 0.5 (np.round, :104), bit2 a direction
+        // value within near_tol of +-0.5 (th_round, :105), bit3 a 2x2-pooled raw qt value within near_tol of 0.5 / 1.5 / 2.5
+        // (Metrics.py:631-632; only when the raw qt map is supplied)
+        unsigned near = 0;
         for (int k = lane; k < 192; k += 32) {
             float4 a = __ldg(bt4 + k), c = __ldg(di4 + k);
             float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
@@ -342,8 +366,15 @@ map2partition_kernel(const uint8_t *__restrict__ qt, const float *__restrict__ b
                 (&wm.rb[0][0])[p] = (int8_t)(int)r;
                 (&wm.rd[0][0])[p] = cv[e] >= 0.5f ? (int8_t)1 : (cv[e] <= -0.5f ? (int8_t)-1 : (int8_t)0);
                 (&wm.outd[0][0])[p] = 0;
+                near |= (fabsf(av[e] - floorf(av[e]) - 0.5f) < near_tol ? 2u : 0u) | (fabsf(fabsf(cv[e]) - 0.5f) < near_tol ? 4u : 0u);
             }
         }
+        if (qt_raw && lane < 16) {
+            const float *q = qt_raw + (size_t)b * 64 + (lane >> 2) * 16 + (lane & 3) * 2;
+            const float mx = fmaxf(fmaxf(q[0], q[1]), fmaxf(q[8], q[9]));
+            if (mx > 0.f && mx < 3.f && fabsf(mx - floorf(mx) - 0.5f) < near_tol) near |= 8u;
+        }
+        near = __reduce_or_sync(0xffffffffu, near);
         for (int k = lane; k < 64; k += 32) wm.qt[k] = qt[(size_t)b * 64 + k];
         for (int k = lane; k < 2 * (17 * 17 + 3); k += 32) (&wm.par[0][0])[k] = 0;
         __syncwarp();
@@ -364,7 +395,7 @@ map2partition_kernel(const uint8_t *__restrict__ qt, const float *__restrict__ b
                 if (!active) continue;
                 int cur = wm.qt[qx * 8 + qy];
                 if (cur == depth) {
-                    Cost c = best_cu<0>(wm, lane, 2 * qx, 2 * qy, 2 * size, 2 * size, 0, cf);
+                    Cost c = best_cu<0>(wm, lb, lane, 2 * qx, 2 * qy, 2 * size, 2 * size, 0, cf);
                     apply_tree<0>(wm, lane, 2 * qx, 2 * qy, 2 * size, 2 * size, c.modes);
                     // float32 evaluation noise of the reference scales with the region total
                     i64 tol = (c.e5 >> 19) + 4096;
@@ -390,16 +421,22 @@ map2partition_kernel(const uint8_t *__restrict__ qt, const float *__restrict__ b
         const int *od4 = reinterpret_cast<const int *>(&wm.outd[0][0]);
         int *g4 = reinterpret_cast<int *>(dout + (size_t)b * 768);
         for (int k = lane; k < 192; k += 32) g4[k] = od4[k];
-        if (flags && lane == 0) flags[b] = (mingap == 0 ? 1u : 0u) | ((unsigned)regions << 8);
+        if (flags && lane == 0) flags[b] = (mingap == 0 ? 1u : 0u) | near | ((unsigned)regions << 8);
         __syncwarp();
     }
 }
 
 int map2partition(Handle *h, const uint8_t *qt, const float *bt, const float *dire, int B, int cf, uint8_t *hor,
-                  uint8_t *ver, int8_t *dout, uint32_t *flags, cudaStream_t s)
+                  uint8_t *ver, int8_t *dout, uint32_t *flags, cudaStream_t s, const double *lamb, const float *qt_raw,
+                  float near_tol)
 {
     if (B <= 0) return PMP_OK;
     PMP_CHECK_ARG(cf == 1 || cf == 2, "chroma_factor must be 1 or 2");
+    Lamb lb{0.7, 0.7, 1.5, 0.3, 0.7};            // Map2Partition.py:100 defaults
+    if (lamb) {
+        for (int i = 0; i < 5; i++) PMP_CHECK_ARG(lamb[i] == lamb[i], "lamb thresholds must not be NaN");
+        lb = Lamb{lamb[0], lamb[1], lamb[2], lamb[3], lamb[4]};
+    }
     size_t smem = sizeof(WarpMaps) * DEC_WARPS;
     if (!h->dec_attr_set) {         // function attributes are per device: one handle per device
         PMP_CUDA(cudaFuncSetAttribute(map2partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -409,7 +446,7 @@ int map2partition(Handle *h, const uint8_t *qt, const float *bt, const float *di
     int cap = h->num_sms * 8;
     if (grid > cap) grid = cap;
     ProfScope ps(h, PROF_DECODE, s, 0, (double)B * (64 + 6144 + 1280 + 4));
-    map2partition_kernel<<<grid, DEC_WARPS * 32, smem, s>>>(qt, bt, dire, B, cf, hor, ver, dout, flags);
+    map2partition_kernel<<<grid, DEC_WARPS * 32, smem, s>>>(qt, bt, dire, B, cf, lb, qt_raw, near_tol, hor, ver, dout, flags);
     h->launches++;
     PMP_CUDA(cudaGetLastError());
     return PMP_OK;

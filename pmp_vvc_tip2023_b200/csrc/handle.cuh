@@ -37,7 +37,9 @@ struct EventPair { cudaEvent_t e0, e1; int cls; double flops, bytes; };
 
 struct Handle {
     int device = 0;
-    int engine = PMP_ENGINE_SIMT;
+    int engine = PMP_ENGINE_TC;         // the production engine; PMP_ENGINE_SIMT is the exact-fp32 checker engine
+    float near_tol = 1e-2f;             // near-threshold report of the decode (pmp_set_near_tol): the map parity bar
+    unsigned int *d_status = nullptr;   // device status words: [0] fp16 saturation events of the TC conv epilogues
     int tc_dtype = PMP_TC_FP16;
     int num_sms = 148;
     long long launches = 0;
@@ -60,6 +62,7 @@ struct Handle {
 
 int ensure_arena(Handle *h, size_t bytes);
 int ensure_scratch(Handle *h, size_t bytes);
+int ensure_status(Handle *h);
 
 // ---- nets.cu -----------------------------------------------------------------------------
 int weights_create(Handle *h, int net, const float *const *tensors, const int64_t *numel, int n, int *wset);
@@ -72,7 +75,10 @@ int forward_msbd(Handle *h, int wset, const void *blocks, int in_dtype, const fl
 // ---- decode.cu ---------------------------------------------------------------------------
 int qt_postprocess(Handle *h, const float *qt, int B, float *out_f32, uint8_t *out_u8, cudaStream_t s);
 int map2partition(Handle *h, const uint8_t *qt, const float *bt, const float *dire, int B, int cf,
-                  uint8_t *hor, uint8_t *ver, int8_t *dout, uint32_t *flags, cudaStream_t s);
+                  uint8_t *hor, uint8_t *ver, int8_t *dout, uint32_t *flags, cudaStream_t s,
+                  const double *lamb = nullptr,        // 5 thresholds lamb1..lamb5 or nullptr (reference defaults)
+                  const float *qt_raw = nullptr,       // raw (un-rounded) qt maps for the near-threshold report, or nullptr
+                  float near_tol = 1e-2f);             // flags bits 1..3: a map value within near_tol of a decision threshold
 int assemble_frames(Handle *h, const uint8_t *hor, const uint8_t *ver, const uint8_t *qt, const int8_t *dire,
                     int frames, int bh, int bw, int8_t *out, cudaStream_t s);
 int format_text(Handle *h, const int8_t *values, int64_t n, char *text, int64_t *n_bytes_host, cudaStream_t s);

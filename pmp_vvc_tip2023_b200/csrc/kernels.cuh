@@ -72,4 +72,9 @@ int stem_unroll(Handle *h, const Act &x, const float *qt, int up, int ov, int kw
 // hi and lo halves of cat's extra channel pad_lu(up(qt)) (Model_QBD.py:130-131).
 int stem_shift(Handle *h, const Act &x, const float *qt, int up, int ov, int uw, bool bf16, void *dst, int B, cudaStream_t s);
 
+// FMT_SPLIT [B, C, H, W] -> fp32 NCHW (test hooks)
+int split_to_f32(Handle *h, const Act &src, float *dst, int B, cudaStream_t s);
+// first-layer conv(s) of a net on the TC engine alone (test hook, pmp_debug_stem): out [B,32,S1,S1] fp32
+int debug_stem(Handle *h, int wset, const void *blocks, int in_dtype, const float *qt, int B, float *out, cudaStream_t s);
+
 }  // namespace pmp

@@ -633,4 +633,31 @@ int forward_msbd(Handle *h, int wset, const void *blocks, int in_dtype, const fl
     return n.rc;
 }
 
+// Test hook: only the first-layer conv(s) of the net (conv_q1, or conv_b1_1..3 concatenated; Model_QBD.py:79-80,:130-135)
+// through the TC engine's stem path, converted back to fp32 NCHW [B,32,S1,S1].
+int debug_stem(Handle *h, int wset, const void *blocks, int in_dtype, const float *qt, int B, float *out, cudaStream_t s)
+{
+    auto it = h->wsets.find(wset);
+    if (it == h->wsets.end()) { set_error("unknown weight set %d", wset); return PMP_ERR_STATE; }
+    WeightSet *ws = &it->second;
+    const bool luma = ws->net == PMP_NET_LUMA_Q || ws->net == PMP_NET_LUMA_MSBD;
+    const bool msbd = ws->net == PMP_NET_LUMA_MSBD || ws->net == PMP_NET_CHROMA_MSBD;
+    if (msbd && !qt) { set_error("debug_stem: the MSBD stems need the qt map"); return PMP_ERR_ARG; }
+    const int S0 = luma ? 68 : 34, S1 = luma ? 64 : 32, ov = luma ? 4 : 2, up = luma ? 8 : 4;
+    int rc = PMP_OK;
+    for (int pass = 0; pass < 2 && !rc; pass++) {
+        Net n{h, ws, B, s, pass == 0, true};
+        Act x = input_act(blocks, in_dtype, luma ? (msbd ? 1 : 1) : 3, S0);
+        Act x2 = n.act(32, S1, S1);
+        if (!n.stem_tc(x, msbd ? qt : nullptr, msbd ? up : 1, msbd ? ov : 0, x2, 0.0)) {
+            set_error("debug_stem: the TC stem path is not available for this net");
+            return n.rc ? n.rc : PMP_ERR_UNSUPPORTED;
+        }
+        rc = n.rc;
+        if (!rc && pass == 0) rc = ensure_arena(h, n.peak);
+        if (!rc && pass == 1) rc = split_to_f32(h, x2, out, B, s);
+    }
+    return rc;
+}
+
 }  // namespace pmp

@@ -17,15 +17,31 @@ COMPS = ("Luma", "Chroma")
 
 
 class PartitionPredictor:
-    def __init__(self, device=0, engine="tc", tc_dtype="fp16", chunk=1024):
+    def __init__(self, device=0, engine="tc", tc_dtype="fp16", chunk=1024, near_tol=1e-2):
         if not torch.cuda.is_available():
             raise _lib.PmpError("no CUDA device: pmp_vvc_tip2023_b200 has no CPU fallback")
         self.device = torch.device("cuda", int(device))
-        self.handle = _lib.Handle.get(int(device))
+        # a private handle: engine, weight sets and activation arena belong to this predictor alone (two predictors on
+        # one device -- e.g. a simt-vs-tc comparison -- do not disturb each other or the Model_QBD modules' default handle)
+        self.handle = _lib.Handle(int(device))
         self.set_engine(engine, tc_dtype)
+        self.handle.set_near_tol(near_tol)
         self.chunk = int(chunk)
         self._wsets = {}           # (comp, qp) -> (wset_q, wset_msbd)
         self._copy_stream = None   # device->host copies of finished components overlap the next component's kernels
+        self.last_flags = {}       # (comp, qp) -> per-block decode flags of the last predict_frames call (device int32)
+
+    def close(self):
+        """Free the private handle (weight sets, arena).  Idempotent."""
+        if self.handle is not None:
+            self.handle.close()
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # interpreter shutdown: the library may already be gone
+            pass
 
     def set_engine(self, engine, tc_dtype="fp16"):
         eng = {"simt": _lib.ENGINE_SIMT, "tc": _lib.ENGINE_TC}[engine]
@@ -88,11 +104,24 @@ class PartitionPredictor:
 
     def cut(self, y, u, v, comps=COMPS):
         y, u, v = self.to_device(y), self.to_device(u), self.to_device(v)
-        return ops.cut_blocks(y, u, v, want_luma="Luma" in comps, want_chroma="Chroma" in comps)
+        return ops.cut_blocks(y, u, v, want_luma="Luma" in comps, want_chroma="Chroma" in comps, handle=self.handle)
 
     def predict_blocks(self, comp, qp, blocks, frames, bh, bw, want_maps=False):
         wq, wb = self._wsets[(comp, qp)]
-        return ops.run_component(wq, wb, comp == "Luma", blocks, frames, bh, bw, self.chunk, want_maps)
+        res = ops.run_component(wq, wb, comp == "Luma", blocks, frames, bh, bw, self.chunk, want_maps,
+                                want_flags=not want_maps, handle=self.handle)
+        self.last_flags[(comp, qp)] = res[-1]
+        return res if want_maps else res[0]
+
+    def counts(self):
+        """Decode report of the last ``predict_frames`` call (synchronises): per (comp, qp) and in total, the number of
+        64x64 blocks whose argmin was a float32 near-tie (``near_tie_blocks``) and whose maps hold a value within
+        ``near_tol`` of a decision threshold (``near_threshold_blocks``) -- the blocks whose integer output may
+        legitimately differ from a float32 evaluation of the reference; plus the fp16 range-guard events."""
+        per = {"%s_QP%d" % k: ops.flag_counts(f) for k, f in self.last_flags.items()}
+        tot = {key: sum(c[key] for c in per.values()) for key in ("blocks", "near_tie_blocks", "near_threshold_blocks")}
+        tot["fp16_saturation_events"] = self.handle.saturation_count()
+        return {"total": tot, "per_component_qp": per}
 
     def predict_frames(self, y, u, v, qps=(32,), comps=COMPS, want_maps=False, host_out=None):
         """y [F,H,W], u/v [F,H/2,W/2] (uint8, or uint16/int16 holding 10-bit samples), host or device.
@@ -133,7 +162,7 @@ class PartitionPredictor:
         return os.path.join(save_dir, "%s_%s_QP%d_PartitionMat.txt" % (seq_path_name, comp, qp))
 
     def write_partition_file(self, values, path):
-        text = ops.format_text(values)
+        text = ops.format_text(values, handle=self.handle)
         with open(path, "wb") as fp:
             fp.write(text.cpu().numpy().tobytes())
         return int(text.numel())

@@ -94,3 +94,31 @@ def net_blocks():
 
 def pipeline_frames():
     return synth.synth_yuv420(PIPE_W, PIPE_H, PIPE_F, seed=4)
+
+
+def value_block_ids(frames, bh, bw):
+    """Block id (frame-major raster) of every value of the per-frame PartitionMat vectors (hor | ver | qt | dire,
+    Map2Partition.py:401-412), flattened over frames: maps a differing file line back to its 64x64 block."""
+    R, C = 16 * bh, 16 * bw
+    r16 = (np.arange(R)[:, None] // 16) * bw + (np.arange(C)[None, :] // 16)
+    r8 = (np.arange(R // 2)[:, None] // 8) * bw + (np.arange(C // 2)[None, :] // 8)
+    per = np.concatenate([r16.reshape(-1), r16.reshape(-1), r8.reshape(-1), np.tile(r16.reshape(-1), 3)])
+    return (np.arange(frames)[:, None] * (bh * bw) + per[None, :]).reshape(-1)
+
+
+def threshold_distance(qt, bt, dire):
+    """Per block: the smallest distance of any map value to a decision threshold of the integer path -- the 2x2-pooled
+    raw qt to 0.5/1.5/2.5 (Metrics.py:631-632), bt to k+0.5 (np.round, Map2Partition.py:104), dire to +-0.5 (:105)."""
+    n = bt.shape[0]
+    q = qt.reshape(n, 4, 2, 4, 2).max(axis=(2, 4)).reshape(n, -1)
+    dq = np.where((q > 0) & (q < 3), np.abs(q - np.floor(q) - 0.5), np.inf).min(axis=1)
+    b = bt.reshape(n, -1)
+    db = np.abs(b - np.floor(b) - 0.5).min(axis=1)
+    dd = np.abs(np.abs(dire.reshape(n, -1)) - 0.5).min(axis=1)
+    return np.minimum(np.minimum(dq, db), dd)
+
+
+# non-default Map_to_Partition constructor thresholds (Map2Partition.py:100) exercised against the reference
+LAMB_SETS = {"a": (0.6, 0.8, 1.2, 0.4, 0.6), "b": (0.9, 0.5, 2.0, 0.2, 0.8), "c": (0.5, 0.9, 1.0, 0.5, 0.5)}
+LAMB_FAMILIES = ("struct_luma_s15", "struct_chroma_s30", "smooth_luma", "quant_chroma")
+LAMB_BLOCKS = 40

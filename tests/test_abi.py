@@ -34,7 +34,7 @@ def test_header_symbols_exported_and_bound(lib):
         assert hasattr(lib, n), "libpmp_b200.so does not export %s" % n
         assert n in _lib.SIGNATURES, "%s has no ctypes signature" % n
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.pmp_version() == 100
+    assert lib.pmp_version() == 200
 
 
 def test_frame_values(lib):

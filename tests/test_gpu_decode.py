@@ -60,6 +60,76 @@ def test_decode_matches_c_oracle_large(chroma, sigma):
     assert regions.min() >= 0 and regions.max() <= 64
 
 
+@pytest.mark.parametrize("tag", sorted(cases.LAMB_SETS))
+def test_decode_nondefault_lamb_matches_reference_golden(tag):
+    """The constructor thresholds lamb1..lamb5 (Map2Partition.py:100) are kernel arguments: goldens from the reference's
+    Map_to_Partition(qt, bt, dire, cf, *lamb).get_partition(), through ops and through the drop-in class."""
+    g = np.load(os.path.join(GOLDEN, "decode_lamb_golden.npz"))
+    lamb = cases.LAMB_SETS[tag]
+    allc = cases.decode_cases()
+    for fam in cases.LAMB_FAMILIES:
+        qt, bt, dire, cf = allc[fam]
+        n = cases.LAMB_BLOCKS
+        hor, ver, dout = _unpack(g, "%s_%s" % (tag, fam), n)
+        h, v, d, flags = ops.map2partition(_cuda(qt[:n].astype(np.uint8).reshape(-1, 64)), _cuda(bt[:n]), _cuda(dire[:n]), cf,
+                                           lamb=lamb)
+        h, v, d, flags = h.cpu().numpy(), v.cpu().numpy(), d.cpu().numpy(), flags.cpu().numpy()
+        bad = [b for b in range(n)
+               if not (np.array_equal(h[b], hor[b]) and np.array_equal(v[b], ver[b]) and np.array_equal(d[b], dout[b]))]
+        assert not [b for b in bad if not (flags[b] & 1)], (tag, fam, bad)
+        assert len(bad) <= 1, (tag, fam, bad)
+        par, dd = Map2Partition.Map_to_Partition(qt[3], bt[3], dire[3], cf, *lamb).get_partition()
+        if 3 not in bad:
+            assert np.array_equal(par[0][:16, :16], hor[3]) and np.array_equal(par[1][:16, :16], ver[3]) and np.array_equal(dd, dout[3])
+    # the defaults passed explicitly are the default path
+    qt, bt, dire, cf = allc["struct_luma_s15"]
+    a = ops.map2partition(_cuda(qt.astype(np.uint8).reshape(-1, 64)), _cuda(bt), _cuda(dire), cf)
+    b = ops.map2partition(_cuda(qt.astype(np.uint8).reshape(-1, 64)), _cuda(bt), _cuda(dire), cf, lamb=ops.DEFAULT_LAMB)
+    assert all(torch.equal(x, y) for x, y in zip(a[:3], b[:3]))
+
+
+@pytest.mark.parametrize("tol", [1e-2, 1e-3])
+def test_near_threshold_flags(tol):
+    """flags bits 1..3: a map value within `tol` of a decision threshold (bt: k+0.5, dire: +-0.5, pooled raw qt:
+    0.5/1.5/2.5) -- the north star's "reported count of CTUs whose values fall within tolerance of a decision threshold"."""
+    rng = np.random.default_rng(17)
+    n = 400
+    qt_raw = (rng.standard_normal((n, 1, 8, 8)) * 1.2 + 1.3).astype(np.float32)
+    bt = np.round(rng.uniform(0, 3, (n, 3, 16, 16))).astype(np.float32) + rng.uniform(-0.2, 0.2, (n, 3, 16, 16)).astype(np.float32)
+    dire = np.round(rng.uniform(-1, 1, (n, 3, 16, 16))).astype(np.float32) + rng.uniform(-0.2, 0.2, (n, 3, 16, 16)).astype(np.float32)
+    # plant near-threshold values in known blocks (distance tol/2 and 2*tol)
+    bt[0, 1, 3, 3] = 1.5 + tol / 2; bt[1, 0, 0, 0] = 2.5 - 2 * tol
+    dire[2, 2, 5, 5] = -0.5 + tol / 2; dire[3, 0, 1, 1] = 0.5 + 2 * tol
+    qt_raw[4, 0, 0:2, 0:2] = 1.5 - tol / 2; qt_raw[5, 0, 2:4, 2:4] = 3.2
+    _, qu8 = ops.qt_postprocess(_cuda(qt_raw), want_f32=False)
+    _, _, _, flags = ops.map2partition(qu8, _cuda(bt), _cuda(dire), 1, qt_raw=_cuda(qt_raw), near_tol=tol)
+    f = flags.cpu().numpy()
+    q = qt_raw.reshape(n, 4, 2, 4, 2).max(axis=(2, 4)).reshape(n, -1)
+    want_q = (((q > 0) & (q < 3)) & (np.abs(q - np.floor(q) - 0.5) < np.float32(tol))).any(1)
+    b = bt.reshape(n, -1)
+    want_b = (np.abs(b - np.floor(b) - np.float32(0.5)) < np.float32(tol)).any(1)
+    want_d = (np.abs(np.abs(dire.reshape(n, -1)) - np.float32(0.5)) < np.float32(tol)).any(1)
+    assert np.array_equal((f & 2) != 0, want_b) and np.array_equal((f & 4) != 0, want_d) and np.array_equal((f & 8) != 0, want_q)
+    assert f[0] & 2 and f[2] & 4 and f[4] & 8 and not (f[5] & 8)
+    c = ops.flag_counts(flags)
+    assert c["blocks"] == n and c["near_threshold_blocks"] == int((want_q | want_b | want_d).sum())
+    # without the raw qt map bit 3 stays clear; the plain entry point uses the handle's tolerance (1e-2)
+    _, _, _, f2 = ops.map2partition(qu8, _cuda(bt), _cuda(dire), 1)
+    assert not (f2.cpu().numpy() & 8).any()
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 1000])
+def test_postprocess_ragged_sizes(n):
+    """The coalesced kernel stages 128 blocks per CTA: ragged tails, both outputs, either output alone."""
+    rng = np.random.default_rng(n)
+    q = (rng.standard_normal((n, 1, 8, 8)) * 1.3 + 1.2).astype(np.float32)
+    want = c_decode.qt_postprocess(q)
+    of, ou = ops.qt_postprocess(_cuda(q))
+    assert np.array_equal(of.cpu().numpy(), want) and np.array_equal(ou.cpu().numpy().reshape(-1, 1, 8, 8), want.astype(np.uint8))
+    of2, none = ops.qt_postprocess(_cuda(q), want_u8=False)
+    assert none is None and torch.equal(of2, of)
+
+
 def test_decode_edge_cases():
     # empty batch, single block, ragged tail
     for n in (0, 1, 5):

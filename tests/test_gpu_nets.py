@@ -96,12 +96,18 @@ def test_pipeline_file_matches_reference(engine, tmp_path):
         want = np.loadtxt(os.path.join(GOLDEN, "pipeline_%s_QP32_PartitionMat.txt" % comp), dtype=np.int64)
         got = vals.cpu().numpy().reshape(-1).astype(np.int64)
         assert got.shape == want.shape
-        nbad = int((got != want).sum())
-        if nbad:
-            # only allowed when some map value is within the float tolerance of a rounding threshold
-            near = np.minimum(np.abs(np.abs(g[comp + "_bt"] % 1.0) - 0.5).min(),
-                              np.abs(np.abs(g[comp + "_dire"]) - 0.5).min())
-            assert near < TOL[engine], "%s: %d differing values without a near-threshold map value" % (comp, nbad)
+        # per block: a differing block is excused only if ITS OWN golden maps hold a value closer to a decision threshold
+        # than twice this block's measured map error, or its own argmin was flagged as a float32 near-tie
+        nblk = qt.shape[0]
+        bad_blocks = np.unique(cases.value_block_ids(cases.PIPE_F, cases.PIPE_H // 64, cases.PIPE_W // 64)[got != want])
+        if bad_blocks.size:
+            err_blk = np.max([np.abs(a.cpu().numpy().reshape(nblk, -1) - g[comp + key].reshape(nblk, -1)).max(axis=1)
+                              for a, key in ((qt, "_qt"), (bt, "_bt"), (dire, "_dire"))], axis=0)
+            dist = cases.threshold_distance(g[comp + "_qt"], g[comp + "_bt"], g[comp + "_dire"])
+            tie = (flags.cpu().numpy() & 1) != 0
+            unexcused = [int(b) for b in bad_blocks if not (dist[b] <= 2 * err_blk[b] + 1e-7 or tie[b])]
+            assert not unexcused, "%s: blocks %s differ from the reference file without a near-threshold value" % (comp, unexcused)
+            assert bad_blocks.size <= max(1, nblk // 50), "%s: %d of %d blocks differ" % (comp, bad_blocks.size, nblk)
         path = str(tmp_path / "f.txt")
         pp.write_partition_file(vals, path)
         assert np.array_equal(np.loadtxt(path, dtype=np.int64), got)
@@ -236,3 +242,102 @@ def test_predict_frames_host_out_matches_device_results():
         for k in ref:
             assert torch.equal(res[k].cpu(), ref[k].cpu())
             assert torch.equal(host[k], ref[k].cpu()), k
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Parity at the bench configuration: the oracle (oracle.nets_ref = the reference's forwards restated in plain torch, CPU
+# fp32, pinned to the reference by tests/golden) run LIVE on this host against the TC engine on one full 1080p frame
+# (480 blocks) per net, and on 256 textured blocks at the worst-case QPs of SURVEY 7.3 -- the precision tail sits in ~4 %
+# knife-edge blocks that 8 golden blocks cannot see.  Bar: max-abs <= 1e-2 (north star); the measured value is printed.
+# ---------------------------------------------------------------------------------------------------------------------
+def _oracle_and_gpu(comp, qp, by, bu, bv, engine="tc"):
+    luma = comp == "Luma"
+    x = torch.from_numpy(by.astype(np.float32)).unsqueeze(1) if luma else nets_ref.chroma_net_input(by, bu, bv)
+    sdq = load_reference_pkl(os.path.join(ROOT, "trained_models", "%s_Q_%d.pkl" % (comp, qp)))
+    sdb_np = synth.seeded_state_dict(comp + "_MSBD", cases.msbd_seed(comp, qp))
+    sdb = {k: torch.from_numpy(v) for k, v in sdb_np.items()}
+    torch.set_num_threads(max(1, min(32, os.cpu_count() or 1)))
+    want_qt, want_bt, want_dire = nets_ref.predict_maps(sdq, sdb, x, luma, batch=120)
+    pp = PartitionPredictor(0, engine=engine, chunk=200)            # ragged chunks: 200 + 200 + 80
+    pp.load_state_dicts(comp, qp, sdq, sdb_np)
+    wq, wb = pp._wsets[(comp, qp)]
+    xu8 = x.to(torch.uint8).cuda()
+    qt, bt, dire = ops.predict_maps(wq, wb, xu8, handle=pp.handle)
+    torch.cuda.synchronize()
+    errs = {"qt": float((qt.cpu() - want_qt).abs().max()), "bt": float((bt.cpu() - want_bt).abs().max()),
+            "dire": float((dire.cpu() - want_dire).abs().max())}
+    sat = pp.handle.saturation_count()
+    pp.close()
+    return errs, sat, (want_qt, want_bt, want_dire), (qt.cpu(), bt.cpu(), dire.cpu())
+
+
+@pytest.mark.parametrize("comp,qp", [("Luma", 22), ("Luma", 37), ("Chroma", 22), ("Chroma", 32)])
+def test_full_1080p_frame_matches_live_oracle(comp, qp):
+    y, u, v = synth.synth_yuv420(1920, 1080, 1, seed=300 + qp)
+    by, bu, bv = nets_ref.cut_blocks(y, u, v, True)
+    assert by.shape[0] == 480
+    errs, sat, want, got = _oracle_and_gpu(comp, qp, by, bu, bv)
+    print("\n[parity] %s QP%d, 480 blocks (one 1080p frame), TC engine vs live CPU-fp32 oracle: max-abs qt %.3e bt %.3e dire %.3e"
+          % (comp, qp, errs["qt"], errs["bt"], errs["dire"]))
+    assert sat == 0, "fp16 saturation events: %d" % sat
+    assert max(errs.values()) <= 1e-2, errs
+    # integer path on top: post-processed qt equal except blocks within the measured error of a rounding threshold
+    qi_want = c_decode_qt(want[0].numpy())
+    qi_got = c_decode_qt(got[0].numpy())
+    diff = np.nonzero((qi_want != qi_got).reshape(480, -1).any(1))[0]
+    dist = cases.threshold_distance(want[0].numpy(), np.zeros((480, 1), np.float32), np.zeros((480, 1), np.float32))   # qt only
+    assert all(dist[b] <= 2 * errs["qt"] + 1e-7 for b in diff), diff
+
+
+def c_decode_qt(q):
+    from oracle import c_decode
+    return c_decode.qt_postprocess(q)
+
+
+@pytest.mark.parametrize("qp", [22, 37])
+def test_textured_blocks_worst_case_qps(qp):
+    """>= 256 textured blocks on the Luma Q + MSBD nets at QP 22 / 37 (the survey's worst cases for reduced precision)."""
+    by, bu, bv = synth.synth_blocks(256, seed=50 + qp)
+    by8 = np.clip(by, 0, 255).astype(np.uint8)
+    errs, sat, _, _ = _oracle_and_gpu("Luma", qp, by8, None, None)
+    print("\n[parity] Luma QP%d, 256 textured blocks: max-abs qt %.3e bt %.3e dire %.3e" % (qp, errs["qt"], errs["bt"], errs["dire"]))
+    assert sat == 0 and max(errs.values()) <= 1e-2, errs
+
+
+def test_predictors_do_not_share_engine_state():
+    """Two predictors on one device keep their own engine (each owns a handle): a simt-vs-tc comparison really compares
+    two engines, and neither disturbs the Model_QBD modules' default handle."""
+    y, u, v = cases.pipeline_frames()
+    h0 = _lib.Handle.get(0)
+    h0.set_engine(_lib.ENGINE_TC)
+    a = PartitionPredictor(0, engine="tc", chunk=6)
+    b = PartitionPredictor(0, engine="simt", chunk=6)
+    assert a.handle.engine() == _lib.ENGINE_TC and b.handle.engine() == _lib.ENGINE_SIMT and h0.engine() == _lib.ENGINE_TC
+    for pp in (a, b):
+        pp.load_state_dicts("Luma", 32, load_reference_pkl(os.path.join(ROOT, "trained_models", "Luma_Q_32.pkl")),
+                            synth.seeded_state_dict("Luma_MSBD", cases.msbd_seed("Luma", 32)))
+    ra = a.predict_frames(y, u, v, qps=(32,), comps=("Luma",), want_maps=True)[("Luma", 32)]
+    l0 = b.handle.launch_count()
+    rb = b.predict_frames(y, u, v, qps=(32,), comps=("Luma",), want_maps=True)[("Luma", 32)]
+    assert b.handle.launch_count() > l0 and a.handle.engine() == _lib.ENGINE_TC
+    d = float((ra[2] - rb[2]).abs().max())
+    assert 0.0 < d <= 1e-2, d            # different engines: close, but not the same bits
+    c = a.counts()
+    assert c["total"]["blocks"] == 12 and set(c["per_component_qp"]) == {"Luma_QP32"}
+    a.close(); b.close()
+
+
+def test_fp16_saturation_is_reported():
+    """Activations beyond +-65504 cannot be split into fp16 hi/lo: the engine counts them instead of clamping silently."""
+    sdq = {k: torch.from_numpy(v) for k, v in synth.seeded_state_dict("Luma_Q", 3).items()}
+    big = {k: (v * 2000.0 if k.startswith("resblock_q1.left.0") else v) for k, v in sdq.items()}
+    x = torch.from_numpy(np.clip(synth.synth_blocks(4, seed=1)[0], 0, 255).astype(np.float32)).unsqueeze(1).cuda()
+    h = _lib.Handle.get(0)
+    h.set_engine(_lib.ENGINE_TC)
+    h.saturation_count(reset=True)
+    for sd, expect in ((sdq, False), (big, True)):
+        net = Model_QBD.Luma_Q_Net()
+        net.load_state_dict(sd)
+        net.cuda()(x)
+        n = h.saturation_count(reset=True)
+        assert (n > 0) == expect, n

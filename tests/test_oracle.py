@@ -47,6 +47,23 @@ def test_decode_numpy_oracle_matches_reference(decode_golden, name):
         assert np.array_equal(h, hor[b]) and np.array_equal(v, ver[b]) and np.array_equal(d, dout[b]), (name, b)
 
 
+@pytest.mark.parametrize("tag", sorted(cases.LAMB_SETS))
+def test_decode_oracles_match_reference_nondefault_lamb(tag):
+    """Map_to_Partition(..., lamb1..lamb5) with non-default constructor thresholds (Map2Partition.py:100)."""
+    g = np.load(os.path.join(GOLDEN, "decode_lamb_golden.npz"))
+    lamb = cases.LAMB_SETS[tag]
+    allc = cases.decode_cases()
+    for fam in cases.LAMB_FAMILIES:
+        qt, bt, dire, cf = allc[fam]
+        n = cases.LAMB_BLOCKS
+        hor, ver, dout = _unpack(g, "%s_%s" % (tag, fam), n)
+        h, v, d = c_decode.map_to_partition_batch(qt[:n], bt[:n], dire[:n], cf, lamb=lamb)
+        assert np.array_equal(h, hor) and np.array_equal(v, ver) and np.array_equal(d, dout), (tag, fam)
+        for b in range(0, n, 13):
+            h1, v1, d1 = decode_ref.map_to_partition(qt[b], bt[b], dire[b], cf, lamb)
+            assert np.array_equal(h1, hor[b]) and np.array_equal(v1, ver[b]) and np.array_equal(d1, dout[b]), (tag, fam, b)
+
+
 def test_postproc_oracles_match_reference():
     g = np.load(os.path.join(GOLDEN, "postproc_golden.npz"))
     q = cases.postproc_inputs()
