@@ -411,7 +411,8 @@ def fourk_main(args):
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     counts = pp.counts()["total"]
-    cnt = torch.tensor([counts["blocks"], counts["near_tie_blocks"], counts["near_threshold_blocks"], counts["fp16_saturation_events"]],
+    cnt = torch.tensor([counts["blocks"], counts["near_tie_blocks"], counts["near_threshold_blocks"], counts["fp16_saturation_events"],
+                        counts["near_threshold_blocks_tight"]],
                        dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(cnt)
@@ -460,7 +461,8 @@ def fourk_main(args):
            "file_write": {"ms": 1e3 * t_write, "bytes": int(nbytes), "e2e_plus_write_ctu_per_s": units / (ms_e2e * 1e-3 / args.steps + t_write)},
            "text_sha256_16": sha, "verified_equal_to_single_gpu": verified,
            "decode_report": {"near_tol": 1e-2, "block_qps": int(cnt[0]), "near_tie_blocks": int(cnt[1]),
-                             "near_threshold_blocks": int(cnt[2]), "fp16_saturation_events": int(cnt[3])}}
+                             "near_threshold_blocks": int(cnt[2]), "near_threshold_blocks_tight_1e-4": int(cnt[4]),
+                             "fp16_saturation_events": int(cnt[3])}}
     print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -483,7 +485,7 @@ def main():
     ap.add_argument("--verify", action="store_true", help="4k30: rank 0 recomputes the whole sequence alone and compares bytes")
     ap.add_argument("--out-dir", type=str, default=None, help="4k30 / text_write: where PartitionMat files are written (default: a temp dir)")
     ap.add_argument("--engine", type=str, default="tc", choices=["tc", "simt"])
-    ap.add_argument("--chunk", type=int, default=2400)
+    ap.add_argument("--chunk", type=int, default=4800)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     args = ap.parse_args()
@@ -618,11 +620,14 @@ def main():
     tot = decode_report["total"]
     out["decode_report"] = {"near_tol": 1e-2, "block_qps": tot["blocks"], "near_tie_blocks": tot["near_tie_blocks"],
                             "near_threshold_blocks": tot["near_threshold_blocks"],
+                            "near_tight_tol": 1e-4, "near_threshold_blocks_tight": tot["near_threshold_blocks_tight"],
                             "near_tie_ctus_upper_bound": min(tot["near_tie_blocks"], tot["blocks"] // 4),
                             "fp16_saturation_events": tot["fp16_saturation_events"],
                             "note": "per 64x64 block and QP over the last step (a 128x128 CTU = 4 blocks): near_tie = the "
                                     "argmin's runner-up lies within the reference's float32 evaluation noise (flags bit 0); "
-                                    "near_threshold = a map value within near_tol of a rounding threshold (bits 1-3). Only "
+                                    "near_threshold = a map value within near_tol of a rounding threshold (bits 1-3; with ~1,600 map values per block "
+                                    "nearly every block has one at 1e-2, hence the second count at near_tight_tol = 2x the "
+                                    "largest measured map error, bits 4-6). Only "
                                     "these blocks may legitimately differ from a float32 evaluation of the reference."}
     if text_leg:
         sec = (text_leg["format_ms"] + text_leg["d2h_ms"] + text_leg["file_write_ms"]) * 1e-3

@@ -106,8 +106,9 @@ int pmp_qt_postprocess(pmp_handle *h, const float *qt, int B, float *out_f32, ui
  * of the reference (result may legitimately differ from a float32 evaluation); bit1 = a depth value lies
  * within near_tol of a rounding threshold k+0.5 (np.round, Map2Partition.py:104); bit2 = a direction
  * value lies within near_tol of +-0.5 (th_round, :30-35,:105); bit3 = a 2x2-pooled raw qt value lies
- * within near_tol of 0.5/1.5/2.5 (Metrics.py:631-632; only when qt_raw is given); bits 8.. = number of
- * MTT regions decoded.  near_tol = the handle's (pmp_set_near_tol). */
+ * within near_tol of 0.5/1.5/2.5 (Metrics.py:631-632; only when qt_raw is given); bits 4..6 = the tests of
+ * bits 1..3 at the tighter tolerance near_tol / 100; bits 8.. = number of MTT regions decoded.
+ * near_tol = the handle's (pmp_set_near_tol). */
 int pmp_map2partition(pmp_handle *h, const uint8_t *qt_u8, const float *bt, const float *dire, int B,
                       int chroma_factor, uint8_t *hor, uint8_t *ver, int8_t *dire_out, uint32_t *flags,
                       void *stream);

@@ -155,13 +155,16 @@ def inference_VVC_seqs(args):
             futs = {g: pool.submit(_predict_shard, preds[g], y[bounds[g]:bounds[g + 1]], u[bounds[g]:bounds[g + 1]],
                                    v[bounds[g]:bounds[g + 1]], qps) for g in shards}
             results = {g: f.result() for g, f in futs.items()}
-        tot = {"blocks": 0, "near_tie_blocks": 0, "near_threshold_blocks": 0, "fp16_saturation_events": 0}
+        tot = {"blocks": 0, "near_tie_blocks": 0, "near_threshold_blocks": 0, "near_threshold_blocks_tight": 0,
+               "fp16_saturation_events": 0}
         for g in shards:
             for key in tot:
                 tot[key] += results[g][2]["total"][key]
+        near_tol = getattr(args, "nearTol", 1e-2)
         print("Decode report: %d block-QPs, %d float32 near-tie argmins, %d with a map value within %g of a decision "
-              "threshold, %d fp16 saturation events" % (tot["blocks"], tot["near_tie_blocks"], tot["near_threshold_blocks"],
-                                                        getattr(args, "nearTol", 1e-2), tot["fp16_saturation_events"]))
+              "threshold (%d within %g), %d fp16 saturation events" % (
+                  tot["blocks"], tot["near_tie_blocks"], tot["near_threshold_blocks"], near_tol,
+                  tot["near_threshold_blocks_tight"], 0.01 * near_tol, tot["fp16_saturation_events"]))
         if tot["fp16_saturation_events"]:
             raise RuntimeError("activations left the fp16 range (%d events): results are clamped; rerun with --tcDtype bf16"
                                % tot["fp16_saturation_events"])

@@ -44,6 +44,19 @@ namespace pmp {
 constexpr int TC_THREADS = 448;
 constexpr int TC_MMA_WARPS = 4;
 constexpr int TC_EPI_WARPS = 8;
+// CTA-pair kernel: two epilogue groups of TC_EPI_WARPS warps each; consecutive accumulator uses (M-tiles) alternate between
+// them, so two M-tiles drain concurrently (measured: with one group the epilogue paced every Cout <= 32 layer and every
+// layer with a residual / attention operand, profiles/r02_epilogue_groups.md)
+constexpr int TC_PAIR_EPI_GROUPS = 2;
+// Warp roles of the pair kernel by warpgroup (setmaxnreg works on whole warpgroups): WG0 = warp 0 weight producer, warp 1
+// activation producer + TMEM owner, warps 2-3 idle; WG1 = warps 4-7 MMA issuers; WG2-5 = warps 8-23 epilogue.  The
+// kernel launches with 80 registers per thread (768 threads); the producers drop to 32, the issuers to 64 and the
+// epilogue warps grow to 104 (128*32 + 128*64 + 512*104 = 64 K registers).
+constexpr int TC_PAIR_ISSUER_WARP0 = 4;
+constexpr int TC_PAIR_EPI_WARP0 = 8;
+constexpr int TC_PAIR_THREADS = 32 * (TC_PAIR_EPI_WARP0 + TC_PAIR_EPI_GROUPS * TC_EPI_WARPS);
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int TC_MAX_STAGES = 24;
 constexpr int TC_MAX_GROUPS = 8;
 constexpr uint32_t TC_SMEM_HEADER = 1024;
@@ -464,20 +477,42 @@ __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t tadd
         }
     }
     float v[CH][8];
+    if constexpr (CH <= 2) {
+        // pair kernel (CH <= 2 per call, 104 registers): every TMEM load of the call in flight before the one wait
+        uint32_t a[CH][8], b[CH][8];
 #pragma unroll
-    for (int j = 0; j < CH; j++) {         // per chunk: small transient register footprint (TMEM latency is short)
-        uint32_t a[8];
-        tmem_ld8(taddr + 8 * (ch0 + j), a);
+        for (int j = 0; j < CH; j++) tmem_ld8(taddr + 8 * (ch0 + j), a[j]);
         if (p.stacked) {        // columns [Cout, 2*Cout) hold a_hi * w_lo
-            uint32_t b[8];
-            tmem_ld8(taddr + p.coutp + 8 * (ch0 + j), b);
+#pragma unroll
+            for (int j = 0; j < CH; j++) tmem_ld8(taddr + p.coutp + 8 * (ch0 + j), b[j]);
             tmem_wait_ld();
 #pragma unroll
-            for (int e = 0; e < 8; e++) v[j][e] = __uint_as_float(a[e]) + __uint_as_float(b[e]);
+            for (int j = 0; j < CH; j++)
+#pragma unroll
+                for (int e = 0; e < 8; e++) v[j][e] = __uint_as_float(a[j][e]) + __uint_as_float(b[j][e]);
         } else {
             tmem_wait_ld();
 #pragma unroll
-            for (int e = 0; e < 8; e++) v[j][e] = __uint_as_float(a[e]);
+            for (int j = 0; j < CH; j++)
+#pragma unroll
+                for (int e = 0; e < 8; e++) v[j][e] = __uint_as_float(a[j][e]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < CH; j++) {         // per chunk: small transient register footprint (TMEM latency is short)
+            uint32_t a[8];
+            tmem_ld8(taddr + 8 * (ch0 + j), a);
+            if (p.stacked) {
+                uint32_t b[8];
+                tmem_ld8(taddr + p.coutp + 8 * (ch0 + j), b);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 8; e++) v[j][e] = __uint_as_float(a[e]) + __uint_as_float(b[e]);
+            } else {
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 8; e++) v[j][e] = __uint_as_float(a[e]);
+            }
         }
     }
     if (p.hpool) {
@@ -1000,7 +1035,7 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
     }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_PAIR_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap2, const __grid_constant__ CUtensorMap tmap_w2, const TcParams p)
 {
@@ -1042,7 +1077,10 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    if (warp == 0) {
+    // (setmaxnreg sits inside each role's branch: ptxas budgets a region by the setmaxnreg that dominates it)
+    if (warp < TC_PAIR_ISSUER_WARP0) {
+      reg_dealloc<32>();
+      if (warp == 0) {
         if (lane == 0) {
             // ===== weight producer: this CTA's half of every (group, filter row) stage; bytes are counted on the leader =====
             const int rows_per_item = p.kh * (p.kw / p.kws) * p.groups;          // ring stages per tile
@@ -1068,7 +1106,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             }
             if (prof) g_tc_stalls[blockIdx.x * TC_PROF_SLOTS + 4] = st;
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         if (lane == 0) {
             // ===== activation producer (own image), bytes counted on the leader's act_full =====
             const uint32_t lead_afull = mapa_cluster(b.afull, 0);
@@ -1096,10 +1134,12 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             }
             if (prof) g_tc_stalls[blockIdx.x * TC_PROF_SLOTS + 5] = st;
         }
-    } else if (warp < 2 + TC_MMA_WARPS) {
+      }     // warps 2-3 of warpgroup 0 are idle: they only donate their registers
+    } else if (warp < TC_PAIR_EPI_WARP0) {
+        reg_dealloc<64>();
         if (rank == 0) {
             // ===== MMA issuers (leader only) =====
-            const int m = warp - 2;
+            const int m = warp - TC_PAIR_ISSUER_WARP0;
             const uint32_t aa = smem_u32(act), ra = smem_u32(ring);
             if (p.stacked) {
                 if (p.kws == 3) pair_issuer<3, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
@@ -1112,41 +1152,50 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             }
         }
     } else {
+        reg_alloc<104>();
         // ===== epilogue (both CTAs, own accumulators; the drain is reported to the leader) =====
-        const int quarter = warp & 3, half = (warp - 2 - TC_MMA_WARPS) >> 2;
+        // Two groups of 8 warps; accumulator use c (running count over items and M-tile slots) goes to group c & 1.  The
+        // slot of use c is c % nslot (nslot is 4 or 8), so a slot always belongs to the same group and the group sees
+        // every phase of its barriers.
+        const int ew = warp - TC_PAIR_EPI_WARP0;
+        const int quarter = warp & 3, half = (ew >> 2) & 1;
+        const uint32_t grp = (uint32_t)ew >> 3;
         const int nchunk = p.coutp >> 3, chh = nchunk >> 1, ch0 = half * chh;
         const uint32_t lead_accempty = mapa_cluster(b.accempty, 0);
+        const uint32_t slot_mask = (uint32_t)p.nslot - 1u, slot_shift = p.nslot == 8 ? 3u : 2u;
         long long st = 0;
-        uint32_t slot0 = 0, ph0 = 0;            // accumulator slot of this tile's M-tile 0, parity of its use count
+        uint32_t c = 0;
         for (int item = cid; item < p.pair_items; item += ncl) {
             const PairGeom t = pair_geom(p, item, (int)rank);
             if ((p.res.p || p.mul.p) && (lane & 7) == 0) {
                 const size_t plane = (size_t)p.H * p.W;
                 for (int mt = 0; mt < t.mt_count; mt++) {
+                    if (((c + (uint32_t)mt) & 1u) != grp) continue;
                     const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
-                    const int r = pos / p.P, c = pos - r * p.P;
-                    if (c < p.W && r < p.H) {
+                    const int r = pos / p.P, cc = pos - r * p.P;
+                    if (cc < p.W && r < p.H) {
                         for (int j = 0; j < chh; j++) {
-                            const size_t o = ((size_t)t.n * (p.out.Cp >> 2) + split_plane(ch0 + j, 0)) * plane + (size_t)r * p.W + c;
+                            const size_t o = ((size_t)t.n * (p.out.Cp >> 2) + split_plane(ch0 + j, 0)) * plane + (size_t)r * p.W + cc;
                             if (p.res.p) { prefetch_l2(reinterpret_cast<const uint4 *>(p.res.p) + o); prefetch_l2(reinterpret_cast<const uint4 *>(p.res.p) + o + 2 * plane); }
                             if (p.mul.p) { prefetch_l2(reinterpret_cast<const uint4 *>(p.mul.p) + o); prefetch_l2(reinterpret_cast<const uint4 *>(p.mul.p) + o + 2 * plane); }
                         }
                     }
                 }
             }
-            for (int mt = 0; mt < p.mt_alloc; mt++) {
-                uint32_t sl = slot0 + (uint32_t)mt, par = ph0;
-                if (sl >= (uint32_t)p.nslot) { sl -= (uint32_t)p.nslot; par ^= 1u; }
+            for (int mt = 0; mt < p.mt_alloc; mt++, c++) {
+                if ((c & 1u) != grp) continue;
+                const uint32_t sl = c & slot_mask, par = (c >> slot_shift) & 1u;
                 { TC_PROF_BEGIN(prof); mbar_wait_relaxed(b.acc + 8 * sl, par); TC_PROF_END(prof, st); }
                 if (mt < t.mt_count) {
                     tc_fence_after();
                     const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
-                    const int r = pos / p.P, c = pos - r * p.P;
-                    const bool valid = t.store && (c < p.W) && (r < p.H);
+                    const int r = pos / p.P, cc = pos - r * p.P;
+                    const bool valid = t.store && (cc < p.W) && (r < p.H);
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + sl * (uint32_t)p.acc_cols;
-                    if (chh == 4) epilogue_chunks<4>(p, taddr, ch0, t.n, r, c, valid);
+                    if (chh == 4) { epilogue_chunks<2>(p, taddr, ch0, t.n, r, cc, valid); epilogue_chunks<2>(p, taddr, ch0 + 2, t.n, r, cc, valid); }
+                    else if (chh == 2) epilogue_chunks<2>(p, taddr, ch0, t.n, r, cc, valid);
                     else
-                        for (int j = 0; j < chh; j++) epilogue_chunks<1>(p, taddr, ch0 + j, t.n, r, c, valid);
+                        for (int j = 0; j < chh; j++) epilogue_chunks<1>(p, taddr, ch0 + j, t.n, r, cc, valid);
                     tc_fence_before();
                 }
                 __syncwarp();
@@ -1155,10 +1204,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     else mbar_arrive_cluster_relaxed(lead_accempty + 8 * sl);
                 }
             }
-            slot0 += (uint32_t)p.mt_alloc;
-            if (slot0 >= (uint32_t)p.nslot) { slot0 -= (uint32_t)p.nslot; ph0 ^= 1u; }
         }
-        if (prof && lane == 0 && warp == 2 + TC_MMA_WARPS) {
+        if (prof && lane == 0 && warp == TC_PAIR_EPI_WARP0) {
             unsigned long long *o = g_tc_stalls + blockIdx.x * TC_PROF_SLOTS;
             o[6] = st; o[9] = clock64() - t_begin;
         }
@@ -1368,7 +1415,7 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         ProfScope ps(h, PROF_CONV_TC, s, flops, hbm_bytes);
         static const int env_pdl = [] { const char *e = getenv("PMP_TC_PDL"); return e ? atoi(e) : 1; }();
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem_pair; cfg.stream = s;
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_PAIR_THREADS); cfg.dynamicSmemBytes = smem_pair; cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;

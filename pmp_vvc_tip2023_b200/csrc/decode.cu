@@ -351,7 +351,9 @@ map2partition_kernel(const uint8_t *__restrict__ qt, const float *__restrict__ b
         // near-threshold report (north star: "a reported count of CTUs whose values fall within tolerance of a decision
         // threshold"): bit1 a depth value within near_tol of a rounding threshold k + 0.5 (np.round, :104), bit2 a direction
         // value within near_tol of +-0.5 (th_round, :105), bit3 a 2x2-pooled raw qt value within near_tol of 0.5 / 1.5 / 2.5
-        // (Metrics.py:631-632; only when the raw qt map is supplied)
+        // (Metrics.py:631-632; only when the raw qt map is supplied); bits 4-6 the same three tests at near_tol / 100 (with
+        // the default 1e-2 that is 1e-4, twice the largest map error measured for the TC engine)
+        const float tight = 0.01f * near_tol;
         unsigned near = 0;
         for (int k = lane; k < 192; k += 32) {
             float4 a = __ldg(bt4 + k), c = __ldg(di4 + k);
@@ -366,13 +368,15 @@ map2partition_kernel(const uint8_t *__restrict__ qt, const float *__restrict__ b
                 (&wm.rb[0][0])[p] = (int8_t)(int)r;
                 (&wm.rd[0][0])[p] = cv[e] >= 0.5f ? (int8_t)1 : (cv[e] <= -0.5f ? (int8_t)-1 : (int8_t)0);
                 (&wm.outd[0][0])[p] = 0;
-                near |= (fabsf(av[e] - floorf(av[e]) - 0.5f) < near_tol ? 2u : 0u) | (fabsf(fabsf(cv[e]) - 0.5f) < near_tol ? 4u : 0u);
+                const float db = fabsf(av[e] - floorf(av[e]) - 0.5f), dd = fabsf(fabsf(cv[e]) - 0.5f);
+                near |= (db < near_tol ? 2u : 0u) | (dd < near_tol ? 4u : 0u) | (db < tight ? 16u : 0u) | (dd < tight ? 32u : 0u);
             }
         }
         if (qt_raw && lane < 16) {
             const float *q = qt_raw + (size_t)b * 64 + (lane >> 2) * 16 + (lane & 3) * 2;
             const float mx = fmaxf(fmaxf(q[0], q[1]), fmaxf(q[8], q[9]));
-            if (mx > 0.f && mx < 3.f && fabsf(mx - floorf(mx) - 0.5f) < near_tol) near |= 8u;
+            const float dq = fabsf(mx - floorf(mx) - 0.5f);
+            if (mx > 0.f && mx < 3.f) near |= (dq < near_tol ? 8u : 0u) | (dq < tight ? 64u : 0u);
         }
         near = __reduce_or_sync(0xffffffffu, near);
         for (int k = lane; k < 64; k += 32) wm.qt[k] = qt[(size_t)b * 64 + k];

@@ -47,13 +47,16 @@ DEFAULT_LAMB = (0.7, 0.7, 1.5, 0.3, 0.7)          # Map2Partition.py:100
 
 FLAG_NEAR_TIE, FLAG_NEAR_BT, FLAG_NEAR_DIRE, FLAG_NEAR_QT = 1, 2, 4, 8
 FLAG_NEAR_THRESHOLD = FLAG_NEAR_BT | FLAG_NEAR_DIRE | FLAG_NEAR_QT
+FLAG_NEAR_THRESHOLD_TIGHT = FLAG_NEAR_THRESHOLD << 3        # the same three tests at near_tol / 100
 
 
 def flag_counts(flags):
-    """{near_tie_blocks, near_threshold_blocks, blocks} of a flags tensor (pmp_map2partition flags, include/pmp_b200.h)."""
+    """{near_tie_blocks, near_threshold_blocks, near_threshold_blocks_tight, blocks} of a flags tensor
+    (pmp_map2partition flags, include/pmp_b200.h)."""
     f = flags.to(torch.int64)
     return {"blocks": int(f.numel()), "near_tie_blocks": int((f & FLAG_NEAR_TIE).ne(0).sum()),
-            "near_threshold_blocks": int((f & FLAG_NEAR_THRESHOLD).ne(0).sum())}
+            "near_threshold_blocks": int((f & FLAG_NEAR_THRESHOLD).ne(0).sum()),
+            "near_threshold_blocks_tight": int((f & FLAG_NEAR_THRESHOLD_TIGHT).ne(0).sum())}
 
 
 def map2partition(qt_u8, bt, dire, chroma_factor, want_flags=True, lamb=None, qt_raw=None, near_tol=None, handle=None):

@@ -119,7 +119,8 @@ class PartitionPredictor:
         ``near_tol`` of a decision threshold (``near_threshold_blocks``) -- the blocks whose integer output may
         legitimately differ from a float32 evaluation of the reference; plus the fp16 range-guard events."""
         per = {"%s_QP%d" % k: ops.flag_counts(f) for k, f in self.last_flags.items()}
-        tot = {key: sum(c[key] for c in per.values()) for key in ("blocks", "near_tie_blocks", "near_threshold_blocks")}
+        tot = {key: sum(c[key] for c in per.values()) for key in ("blocks", "near_tie_blocks", "near_threshold_blocks",
+                                                              "near_threshold_blocks_tight")}
         tot["fp16_saturation_events"] = self.handle.saturation_count()
         return {"total": tot, "per_component_qp": per}
 

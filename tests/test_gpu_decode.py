@@ -113,6 +113,12 @@ def test_near_threshold_flags(tol):
     assert f[0] & 2 and f[2] & 4 and f[4] & 8 and not (f[5] & 8)
     c = ops.flag_counts(flags)
     assert c["blocks"] == n and c["near_threshold_blocks"] == int((want_q | want_b | want_d).sum())
+    # bits 4-6: the same tests at near_tol / 100
+    t2 = np.float32(0.01) * np.float32(tol)
+    tight_b = (np.abs(b - np.floor(b) - np.float32(0.5)) < t2).any(1)
+    tight_d = (np.abs(np.abs(dire.reshape(n, -1)) - np.float32(0.5)) < t2).any(1)
+    assert np.array_equal((f & 16) != 0, tight_b) and np.array_equal((f & 32) != 0, tight_d)
+    assert c["near_threshold_blocks_tight"] <= c["near_threshold_blocks"]
     # without the raw qt map bit 3 stays clear; the plain entry point uses the handle's tolerance (1e-2)
     _, _, _, f2 = ops.map2partition(qu8, _cuda(bt), _cuda(dire), 1)
     assert not (f2.cpu().numpy() & 8).any()
