@@ -88,13 +88,13 @@ def _parse_cfg(path):
     return seq_path, is10bit
 
 
-def _predict_shard(pred, y, u, v, qps):
+def _predict_shard(pred, y, u, v, qps, want_raw=False):
     """One GPU's frame range: cut once, then per (component, QP) the nets + post-process + decode + frame assembly
     (timed with CUDA events, the counterpart of the reference's per-(QP, comp) inference clock, Inference_QBD.py:210-227)
     and the text formatting + device->host copy (wall clock; the reference's post-process clock, :229-241).
-    Returns ({(comp, qp): bytes}, {(comp, qp): (net_s, post_s)}, counts)."""
+    Returns ({(comp, qp): bytes}, {(comp, qp): (net_s, post_s)}, counts, {(comp, qp): raw int8 bytes} when want_raw)."""
     from . import ops
-    texts, times = {}, {}
+    texts, times, raw = {}, {}, {}
     f, hgt, wid = y.shape
     bh, bw = hgt // 64, wid // 64
     dev = pred.device
@@ -110,9 +110,11 @@ def _predict_shard(pred, y, u, v, qps):
                 e1.synchronize()
                 t0 = time.time()
                 texts[(comp, qp)] = ops.format_text(vals, handle=pred.handle).cpu().numpy().tobytes()
+                if want_raw:
+                    raw[(comp, qp)] = vals.cpu().numpy().tobytes()
                 times[(comp, qp)] = (e0.elapsed_time(e1) * 1e-3, time.time() - t0)
         counts = pred.counts()
-    return texts, times, counts
+    return texts, times, counts, raw
 
 
 @torch.no_grad()
@@ -153,7 +155,7 @@ def inference_VVC_seqs(args):
         # shard must never turn into a silently truncated PartitionMat file
         with ThreadPoolExecutor(max_workers=max(1, len(shards))) as pool:
             futs = {g: pool.submit(_predict_shard, preds[g], y[bounds[g]:bounds[g + 1]], u[bounds[g]:bounds[g + 1]],
-                                   v[bounds[g]:bounds[g + 1]], qps) for g in shards}
+                                   v[bounds[g]:bounds[g + 1]], qps, getattr(args, "binaryOut", False)) for g in shards}
             results = {g: f.result() for g, f in futs.items()}
         tot = {"blocks": 0, "near_tie_blocks": 0, "near_threshold_blocks": 0, "near_threshold_blocks_tight": 0,
                "fp16_saturation_events": 0}
@@ -176,6 +178,14 @@ def inference_VVC_seqs(args):
                 with open(path, "wb") as fp:
                     for g in shards:
                         fp.write(results[g][0][(comp, qp)])           # KeyError if a shard did not deliver
+                if getattr(args, "binaryOut", False):
+                    # opt-in raw int8 form for the VTM-side binary reader (tools/vtm_reader/pmp_partition_reader.h)
+                    from .partition_io import bin_header, values_per_frame
+                    r_, c_, _ = values_per_frame(y.shape[1], y.shape[2])
+                    with open(path[:-4] + ".bin", "wb") as fp:
+                        fp.write(bin_header(y.shape[0], r_, c_))
+                        for g in shards:
+                            fp.write(results[g][3][(comp, qp)])
                 # shards run concurrently: the sequence's time is the slowest GPU's
                 t_net[s, qi, ci] = max(results[g][1][(comp, qp)][0] for g in shards)
                 t_post[s, qi, ci] = max(results[g][1][(comp, qp)][1] for g in shards) + (time.time() - t0)
@@ -209,6 +219,8 @@ def build_parser():
     parser.add_argument('--tcDtype', type=str, default='fp16', choices=['fp16', 'bf16'],
                         help='16-bit operand format of the split-precision tensor-core engine')
     parser.add_argument('--nearTol', type=float, default=1e-2, help='tolerance of the near-threshold block count')
+    parser.add_argument('--binaryOut', action='store_true',
+                        help='also write <seq>_<comp>_QP<qp>_PartitionMat.bin (raw int8) for tools/vtm_reader')
     return parser
 
 

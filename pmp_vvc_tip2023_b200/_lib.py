@@ -5,7 +5,8 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpmp_b200.so")
+# PMP_B200_LIB: file name of another build of the same library inside this directory (kernel A/B runs in one GPU call)
+LIB_PATH = os.path.join(HERE, os.path.basename(os.environ.get("PMP_B200_LIB", "libpmp_b200.so")))
 
 NET_LUMA_Q, NET_LUMA_MSBD, NET_CHROMA_Q, NET_CHROMA_MSBD = 0, 1, 2, 3
 NET_IDS = {"Luma_Q": 0, "Luma_MSBD": 1, "Chroma_Q": 2, "Chroma_MSBD": 3}

@@ -455,20 +455,17 @@ __device__ __forceinline__ void saturation_check(const TcParams &p, const float 
     if (am > 65504.f && !p.out.bf16 && p.sat) atomicAdd(p.sat, 1u);
 }
 
-// Epilogue of one M-tile for CH consecutive 8-channel chunks starting at chunk ch0 (one thread = one position).
+// Epilogue operand fetch of one M-tile position: the residual (or, when there is no residual -- the Att trunks' last block
+// has a fused shortcut -- the attention product's operand, which then takes the residual's registers) for CH consecutive
+// 8-channel chunks.  Issued ahead of the accumulator wait / the TMEM loads so that its latency overlaps them.
 template <int CH>
-__device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t taddr, int ch0, int n, int r, int c, bool valid)
+__device__ __forceinline__ void epilogue_fetch(const TcParams &p, int ch0, int n, int r, int c, bool valid, uint4 *rh, uint4 *rl)
 {
-    const size_t plane = (size_t)p.H * p.W;
-    const size_t pix = (size_t)r * p.W + c;
-    uint4 rh[CH], rl[CH];
-    // residual operand first: its latency overlaps the TMEM loads
-    // (the attention product's operand takes the residual's registers when there is no residual -- the Att trunks' last
-    // block has a fused shortcut -- so that its latency overlaps the TMEM loads too)
     const bool mul_early = p.mul.p && !p.res.p;
     if ((p.res.p || mul_early) && valid) {
+        const size_t plane = (size_t)p.H * p.W;
         const Act &t = p.res.p ? p.res : p.mul;
-        const uint4 *rb = reinterpret_cast<const uint4 *>(t.p) + (size_t)n * (t.Cp >> 2) * plane + pix;
+        const uint4 *rb = reinterpret_cast<const uint4 *>(t.p) + (size_t)n * (t.Cp >> 2) * plane + (size_t)r * p.W + c;
 #pragma unroll
         for (int j = 0; j < CH; j++) {
             const uint4 *q = rb + (size_t)split_plane(ch0 + j, 0) * plane;
@@ -476,6 +473,17 @@ __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t tadd
             rl[j] = ldg_stream(q + 2 * plane);
         }
     }
+}
+
+// Epilogue of one M-tile for CH consecutive 8-channel chunks starting at chunk ch0 (one thread = one position); rh / rl
+// hold what epilogue_fetch<CH> loaded for the same chunks.
+template <int CH>
+__device__ __forceinline__ void epilogue_process(const TcParams &p, uint32_t taddr, int ch0, int n, int r, int c, bool valid,
+                                                 const uint4 *rh, const uint4 *rl)
+{
+    const size_t plane = (size_t)p.H * p.W;
+    const size_t pix = (size_t)r * p.W + c;
+    const bool mul_early = p.mul.p && !p.res.p;
     float v[CH][8];
     if constexpr (CH <= 2) {
         // pair kernel (CH <= 2 per call, 104 registers): every TMEM load of the call in flight before the one wait
@@ -599,6 +607,14 @@ __device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t tadd
         q[2 * plane] = Ll;
     }
     saturation_check<CH>(p, v);
+}
+
+template <int CH>
+__device__ __forceinline__ void epilogue_chunks(const TcParams &p, uint32_t taddr, int ch0, int n, int r, int c, bool valid)
+{
+    uint4 rh[CH], rl[CH];
+    epilogue_fetch<CH>(p, ch0, n, r, c, valid, rh, rl);
+    epilogue_process<CH>(p, taddr, ch0, n, r, c, valid, rh, rl);
 }
 
 // Persistent, warp-specialised: warp 0 weight producer, warp 1 activation producer + TMEM owner, warps 2..5 MMA issuers
@@ -1185,17 +1201,29 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             for (int mt = 0; mt < p.mt_alloc; mt++, c++) {
                 if ((c & 1u) != grp) continue;
                 const uint32_t sl = c & slot_mask, par = (c >> slot_shift) & 1u;
+                const bool work = mt < t.mt_count;
+                const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
+                const int r = pos / p.P, cc = pos - r * p.P;
+                const bool valid = work && t.store && (cc < p.W) && (r < p.H);
+                // residual / attention operands of this thread's chunks: requested before the accumulator wait
+                uint4 rh[4], rl[4];
+                if (work) {
+                    if (chh == 4) epilogue_fetch<4>(p, ch0, t.n, r, cc, valid, rh, rl);
+                    else if (chh == 2) epilogue_fetch<2>(p, ch0, t.n, r, cc, valid, rh, rl);
+                    else epilogue_fetch<1>(p, ch0, t.n, r, cc, valid, rh, rl);
+                }
                 { TC_PROF_BEGIN(prof); mbar_wait_relaxed(b.acc + 8 * sl, par); TC_PROF_END(prof, st); }
-                if (mt < t.mt_count) {
+                if (work) {
                     tc_fence_after();
-                    const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
-                    const int r = pos / p.P, cc = pos - r * p.P;
-                    const bool valid = t.store && (cc < p.W) && (r < p.H);
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + sl * (uint32_t)p.acc_cols;
-                    if (chh == 4) { epilogue_chunks<2>(p, taddr, ch0, t.n, r, cc, valid); epilogue_chunks<2>(p, taddr, ch0 + 2, t.n, r, cc, valid); }
-                    else if (chh == 2) epilogue_chunks<2>(p, taddr, ch0, t.n, r, cc, valid);
-                    else
-                        for (int j = 0; j < chh; j++) epilogue_chunks<1>(p, taddr, ch0 + j, t.n, r, cc, valid);
+                    if (chh == 4) {
+                        epilogue_process<2>(p, taddr, ch0, t.n, r, cc, valid, rh, rl);
+                        epilogue_process<2>(p, taddr, ch0 + 2, t.n, r, cc, valid, rh + 2, rl + 2);
+                    } else if (chh == 2) {
+                        epilogue_process<2>(p, taddr, ch0, t.n, r, cc, valid, rh, rl);
+                    } else {
+                        epilogue_process<1>(p, taddr, ch0, t.n, r, cc, valid, rh, rl);
+                    }
                     tc_fence_before();
                 }
                 __syncwarp();
