@@ -1212,7 +1212,11 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     else if (chh == 2) epilogue_fetch<2>(p, ch0, t.n, r, cc, valid, rh, rl);
                     else epilogue_fetch<1>(p, ch0, t.n, r, cc, valid, rh, rl);
                 }
+#ifdef PMP_EPI_SPIN        // build-time A/B knob: epilogue polls without the back-off
+                { TC_PROF_BEGIN(prof); mbar_wait(b.acc + 8 * sl, par); TC_PROF_END(prof, st); }
+#else
                 { TC_PROF_BEGIN(prof); mbar_wait_relaxed(b.acc + 8 * sl, par); TC_PROF_END(prof, st); }
+#endif
                 if (work) {
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + sl * (uint32_t)p.acc_cols;
