@@ -51,7 +51,7 @@ constexpr int TC_PAIR_EPI_GROUPS = 2;
 // Warp roles of the pair kernel by warpgroup (setmaxnreg works on whole warpgroups): WG0 = warp 0 weight producer, warp 1
 // activation producer + TMEM owner, warps 2-3 idle; WG1 = warps 4-7 MMA issuers; WG2-5 = warps 8-23 epilogue.  The
 // kernel launches with 80 registers per thread (768 threads); the producers drop to 32, the issuers to 64 and the
-// epilogue warps grow to 104 (128*32 + 128*64 + 512*104 = 64 K registers).
+// epilogue warps grow to 96 (128*32 + 128*64 + 512*96 = 768*80: setmaxnreg trades registers inside the pool the CTA launched with).
 constexpr int TC_PAIR_ISSUER_WARP0 = 4;
 constexpr int TC_PAIR_EPI_WARP0 = 8;
 constexpr int TC_PAIR_THREADS = 32 * (TC_PAIR_EPI_WARP0 + TC_PAIR_EPI_GROUPS * TC_EPI_WARPS);
@@ -1168,7 +1168,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             }
         }
     } else {
-        reg_alloc<104>();
+        reg_alloc<96>();
         // ===== epilogue (both CTAs, own accumulators; the drain is reported to the leader) =====
         // Two groups of 8 warps; accumulator use c (running count over items and M-tile slots) goes to group c & 1.  The
         // slot of use c is c % nslot (nslot is 4 or 8), so a slot always belongs to the same group and the group sees
