@@ -11,6 +11,7 @@ are packed into the kernels' operand layouts lazily, once per (device, parameter
 (device, net kind) so that alternating QPs / DataParallel replicas do not re-pack on every forward.
 """
 import ctypes
+import itertools
 from collections import OrderedDict
 
 import torch
@@ -47,6 +48,7 @@ def _make_layer(cin, couts, ks):
 
 _WSET_LRU = 8            # packed weight sets kept per (device, net kind): 4 QPs x (module, DataParallel replica)
 _WSET_CACHE = {}         # (device, net kind) -> OrderedDict{fingerprint: wset id}
+_SERIAL = itertools.count()      # per-instance serial numbers: id() and data_ptr() are both reused after a module dies
 
 
 class _PmpNet(nn.Module):
@@ -55,6 +57,8 @@ class _PmpNet(nn.Module):
 
     def __init__(self):
         super().__init__()
+        self._serial = next(_SERIAL)   # never reused, unlike id(self): a new net whose tensors land on a dead net's
+        #                                addresses (caching allocator) must not hit that net's packed weights
         self._wgen = 0           # bumped by load_state_dict / invalidate_weights(): part of the cache fingerprint
         self._src_fp = None      # set on nn.DataParallel replicas: fingerprint of the module they were replicated from
 
@@ -68,7 +72,7 @@ class _PmpNet(nn.Module):
         return super()._load_from_state_dict(*args, **kwargs)
 
     def _fingerprint(self):
-        return (id(self), self._wgen) + tuple((p.data_ptr(), p._version) for p in self._param_list())
+        return (self._serial, self._wgen) + tuple((p.data_ptr(), p._version) for p in self._param_list())
 
     def _replicate_for_data_parallel(self):
         # runs on the SOURCE module once per replica (torch/nn/parallel/replicate.py): the replica's broadcast weight

@@ -25,10 +25,14 @@
 //                        fused horizontal max-pool, TMA-assembled first-layer ("stem") mode, programmatic dependent launch.
 //   conv_tc_kernel       the first-generation single-CTA kernel (per-tap stages), kept as the PMP_TC_PAIR=0 / self-test
 //                        A-B reference; same arithmetic per accumulator, so both produce the same bits.
-// Warp roles in both (448 threads, persistent grid): warp 0 = weight producer, warp 1 = activation producer + TMEM owner,
-// warps 2-5 = MMA issuers (one per M-tile), warps 6-13 = epilogue (TMEM -> registers -> bias / residual add / ReLU /
-// attention product / pair maximum -> hi/lo split -> coalesced 16-byte stores).
-// What was measured and why each piece exists: profiles/r01_conv_tc_ncu_summary.md, profiles/r01b_conv_tc_pair_summary.md.
+// Warp roles, persistent grid.  conv_tc_kernel (448 threads): warp 0 = weight producer, warp 1 = activation producer + TMEM
+// owner, warps 2-5 = MMA issuers (one per M-tile), warps 6-13 = epilogue.  conv_tc_pair_kernel (768 threads, roles
+// aligned to warpgroups for setmaxnreg: 32 / 64 / 96 registers): warps 0-1 = producers (2-3 idle), warps 4-7 = MMA issuers,
+// warps 8-23 = two epilogue groups of 8 warps draining alternate accumulator slots (TMEM -> registers -> bias / residual
+// add / ReLU / attention product / pair maximum -> hi/lo split -> coalesced 16-byte stores; residual / attention operands
+// are fetched ahead of the accumulator wait).
+// What was measured and why each piece exists: profiles/r01_conv_tc_ncu_summary.md, profiles/r01b_conv_tc_pair_summary.md,
+// profiles/r02_epilogue_groups.md.
 #include "handle.cuh"
 #include "kernels.cuh"
 

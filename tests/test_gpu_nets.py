@@ -191,15 +191,22 @@ def test_cli_driver_writes_reference_files(tmp_path):
         "--jobID", "j1", "--inputDir", str(inp), "--outDir", str(tmp_path / "out"), "--batchSize", "5", "--startSeqID", "0",
         "--seqNum", "1", "--seqInfo", str(tmp_path / "seqs.txt"), "--cfgDir", str(cfg),
         "--modelDir", os.path.join(ROOT, "trained_models"), "--ssRatio", "1", "--missingBD", "seeded",
-        "--gpus", str(min(2, torch.cuda.device_count()))])          # 2 GPUs: one frame each, segments concatenated
+        "--gpus", str(min(2, torch.cuda.device_count())),           # 2 GPUs: one frame each, segments concatenated
+        "--binaryOut"])
     Inference_QBD.inference_VVC_seqs(args)
     out = tmp_path / "out" / "j1" / "PartitionMat"
-    names = sorted(os.listdir(out))
+    names = sorted(n for n in os.listdir(out) if n.endswith(".txt"))
     assert len(names) == 8 and "pipe_192x128_10bit_Luma_QP32_PartitionMat.txt" in names
+    from pmp_vvc_tip2023_b200 import partition_io
     for comp in ("Luma", "Chroma"):
         got = open(out / ("pipe_192x128_10bit_%s_QP32_PartitionMat.txt" % comp), "rb").read()
         want = open(os.path.join(GOLDEN, "pipeline_%s_QP32_PartitionMat.txt" % comp), "rb").read()
         assert got == want
+        # --binaryOut: the raw int8 form for the VTM-side reader holds the same values in the same order
+        vals, rows, cols = partition_io.read_partition_bin(str(out / ("pipe_192x128_10bit_%s_QP32_PartitionMat.bin" % comp)))
+        assert (rows, cols) == (16 * (cases.PIPE_H >> 6), 16 * (cases.PIPE_W >> 6))
+        assert np.array_equal(vals, partition_io.text_to_values(os.path.join(GOLDEN, "pipeline_%s_QP32_PartitionMat.txt" % comp),
+                                                                cases.PIPE_H, cases.PIPE_W))
     assert os.path.exists(tmp_path / "out" / "j1" / "Time_Sta_0_1.txt")
 
 

@@ -39,3 +39,17 @@ def test_param_list_on_dataparallel_replica():
         plist = rep._param_list()
         for p, q in zip(plist, net._param_list()):
             assert isinstance(p, torch.Tensor) and torch.equal(p, q)
+
+
+def test_weight_cache_fingerprint_is_per_instance():
+    """A new net whose parameters land on a dead net's addresses must not reuse that net's packed weights: the cache
+    fingerprint carries a never-reused per-instance serial (id() and data_ptr() are both recycled)."""
+    from pmp_vvc_tip2023_b200 import Model_QBD
+    a = Model_QBD.Chroma_Q_Net()
+    fa = a._fingerprint()
+    del a
+    b = Model_QBD.Chroma_Q_Net()
+    assert b._fingerprint()[0] != fa[0]
+    g0 = b._fingerprint()
+    b.load_state_dict(b.state_dict())
+    assert b._fingerprint() != g0            # load_state_dict invalidates the packed weights
