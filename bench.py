@@ -371,7 +371,8 @@ def fourk_main(args):
         texts = {k: (ops.format_text(res[k], handle=pp.handle) if hi > lo else torch.empty(0, dtype=torch.uint8, device="cuda")) for k in keys}
         if world == 1:
             for k in keys:
-                gathered[k] = texts[k].cpu()
+                gathered[k] = pp.to_host_pinned(("text",) + k, texts[k], sync=False)     # reusable pinned staging
+            torch.cuda.synchronize()
             return
         sizes = torch.tensor([texts[k].numel() for k in keys], dtype=torch.int64, device="cuda")
         all_sizes = [torch.empty_like(sizes) for _ in range(world)]
@@ -379,12 +380,14 @@ def fourk_main(args):
         all_sizes = torch.stack(all_sizes).cpu()                # [world, 8]
         for i, k in enumerate(keys):
             mx = int(all_sizes[:, i].max())
-            buf = torch.zeros(mx, dtype=torch.uint8, device="cuda")
+            buf = torch.empty(mx, dtype=torch.uint8, device="cuda")
             buf[:texts[k].numel()] = texts[k]
             outs = [torch.empty(mx, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
-            dist.gather(buf, outs, dst=0)
+            dist.gather(buf, outs, dst=0)                       # NCCL over NVLink
             if rank == 0:
-                gathered[k] = torch.cat([outs[r][:int(all_sizes[r, i])] for r in range(world)]).cpu()
+                gathered[k] = pp.to_host_pinned(("text",) + k, torch.cat([outs[r][:int(all_sizes[r, i])] for r in range(world)]),
+                                                sync=False)
+        torch.cuda.synchronize()
 
     def timed(fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

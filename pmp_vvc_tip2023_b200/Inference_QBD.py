@@ -92,7 +92,8 @@ def _predict_shard(pred, y, u, v, qps, want_raw=False):
     """One GPU's frame range: cut once, then per (component, QP) the nets + post-process + decode + frame assembly
     (timed with CUDA events, the counterpart of the reference's per-(QP, comp) inference clock, Inference_QBD.py:210-227)
     and the text formatting + device->host copy (wall clock; the reference's post-process clock, :229-241).
-    Returns ({(comp, qp): bytes}, {(comp, qp): (net_s, post_s)}, counts, {(comp, qp): raw int8 bytes} when want_raw)."""
+    Returns ({(comp, qp): uint8 array}, {(comp, qp): (net_s, post_s)}, counts, {(comp, qp): int8 array} when want_raw);
+    the arrays are views of the predictor's pinned staging buffers (valid until its next call)."""
     from . import ops
     texts, times, raw = {}, {}, {}
     f, hgt, wid = y.shape
@@ -109,9 +110,10 @@ def _predict_shard(pred, y, u, v, qps, want_raw=False):
                 e1.record()
                 e1.synchronize()
                 t0 = time.time()
-                texts[(comp, qp)] = ops.format_text(vals, handle=pred.handle).cpu().numpy().tobytes()
+                # pinned staging buffers, reused across sequences; the writer consumes the views before the next sequence
+                texts[(comp, qp)] = pred.to_host_pinned(("text", comp, qp), ops.format_text(vals, handle=pred.handle)).numpy()
                 if want_raw:
-                    raw[(comp, qp)] = vals.cpu().numpy().tobytes()
+                    raw[(comp, qp)] = pred.to_host_pinned(("raw", comp, qp), vals).numpy()
                 times[(comp, qp)] = (e0.elapsed_time(e1) * 1e-3, time.time() - t0)
         counts = pred.counts()
     return texts, times, counts, raw
