@@ -372,6 +372,7 @@ struct TcParams {
     uint32_t plane_bytes, group_bytes, stage_bytes, tmem_cols, idesc1, idesc2;
     int relu, stacked, pairbuf, nbuf, dbg, hpool;
     int nslot, mt_alloc, acc_cols;      // CTA-pair kernel: accumulator slot ring (slots, M-tiles per tile, columns per slot)
+    int epi_groups;                     // CTA-pair kernel: epilogue groups draining accumulator uses round-robin (2 x 8 warps or 4 x 4 warps)
     int aslots, groups2;                // CTA-pair kernel: activation slot ring (one channel-group box each); fused shortcut groups
     // CTA-pair kernel, first-layer ("stem") mode: the A operand is assembled by TMA from 8 pre-shifted copies of each source
     // plane (stem_shift_kernel); a K chunk of 8 unrolled channels = (plane, 8 consecutive kx shifts).  hi planes only.
@@ -1079,7 +1080,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     if (threadIdx.x == 0) {
         for (int g = 0; g < p.aslots; g++) { mbar_init(b.afull + 8 * g, 1); mbar_init(b.aempty + 8 * g, TC_MMA_WARPS); }
         for (int s = 0; s < p.nstages; s++) { mbar_init(b.wfull + 8 * s, 1); mbar_init(b.wempty + 8 * s, TC_MMA_WARPS); }
-        for (int m = 0; m < p.nslot; m++) { mbar_init(b.acc + 8 * m, 1); mbar_init(b.accempty + 8 * m, 2 * TC_EPI_WARPS); }
+        for (int m = 0; m < p.nslot; m++) { mbar_init(b.acc + 8 * m, 1); mbar_init(b.accempty + 8 * m, 2 * (TC_PAIR_EPI_GROUPS * TC_EPI_WARPS / p.epi_groups)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -1174,13 +1175,17 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     } else {
         reg_alloc<96>();
         // ===== epilogue (both CTAs, own accumulators; the drain is reported to the leader) =====
-        // Two groups of 8 warps; accumulator use c (running count over items and M-tile slots) goes to group c & 1.  The
-        // slot of use c is c % nslot (nslot is 4 or 8), so a slot always belongs to the same group and the group sees
-        // every phase of its barriers.
+        // Accumulator use c (running count over items and M-tile slots) goes to group c % G.  The slot of use c is
+        // c % nslot (4 or 8, a multiple of G), so a slot always belongs to the same group and the group sees every phase of
+        // its barriers.  G = 2 groups of 8 warps (two warps per TMEM lane quarter share the channel chunks of a position), or,
+        // for Cout <= 32, G = 4 groups of 4 warps (one warp per lane quarter takes all chunks): those layers are paced by the
+        // epilogue's per-M-tile latency chain, four M-tiles in flight hide more of it than two.
         const int ew = warp - TC_PAIR_EPI_WARP0;
-        const int quarter = warp & 3, half = (ew >> 2) & 1;
-        const uint32_t grp = (uint32_t)ew >> 3;
-        const int nchunk = p.coutp >> 3, chh = nchunk >> 1, ch0 = half * chh;
+        const int quarter = warp & 3;
+        const uint32_t G = (uint32_t)p.epi_groups, gmask = G - 1u;
+        const uint32_t grp = G == 4 ? (uint32_t)ew >> 2 : (uint32_t)ew >> 3;
+        const int half = G == 4 ? 0 : (ew >> 2) & 1;
+        const int nchunk = p.coutp >> 3, chh = G == 4 ? nchunk : nchunk >> 1, ch0 = half * chh;
         const uint32_t lead_accempty = mapa_cluster(b.accempty, 0);
         const uint32_t slot_mask = (uint32_t)p.nslot - 1u, slot_shift = p.nslot == 8 ? 3u : 2u;
         long long st = 0;
@@ -1190,7 +1195,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             if ((p.res.p || p.mul.p) && (lane & 7) == 0) {
                 const size_t plane = (size_t)p.H * p.W;
                 for (int mt = 0; mt < t.mt_count; mt++) {
-                    if (((c + (uint32_t)mt) & 1u) != grp) continue;
+                    if (((c + (uint32_t)mt) & gmask) != grp) continue;
                     const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
                     const int r = pos / p.P, cc = pos - r * p.P;
                     if (cc < p.W && r < p.H) {
@@ -1203,7 +1208,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 }
             }
             for (int mt = 0; mt < p.mt_alloc; mt++, c++) {
-                if ((c & 1u) != grp) continue;
+                if ((c & gmask) != grp) continue;
                 const uint32_t sl = c & slot_mask, par = (c >> slot_shift) & 1u;
                 const bool work = mt < t.mt_count;
                 const int pos = t.q0 + mt * 128 + quarter * 32 + lane;
@@ -1425,6 +1430,8 @@ int conv_tc(Handle *h, const TcConvArgs &a, int B, cudaStream_t s)
         p.acc_cols = (g.stacked ? 2 : 1) * g.coutp;
         p.nslot = 512 / p.acc_cols < 8 ? 512 / p.acc_cols : 8;
         p.mt_alloc = p.nslot < 8 ? 3 : 4;
+        static const int env_epi4 = [] { const char *e = getenv("PMP_TC_EPI4"); return e ? atoi(e) : 1; }();     // A/B knob
+        p.epi_groups = (env_epi4 && g.coutp <= 32 && p.nslot == 8) ? 4 : 2;
         p.tmem_cols = g.tmem_cols;
         tc_ring_layout(g, slab * (uint32_t)kws, a.kh * (a.kw / kws));
         p.nstages = g.nstages; p.nbuf = g.nbuf; p.kws = kws;
