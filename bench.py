@@ -347,13 +347,27 @@ def fourk_main(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pp = load_predictor(local, args.engine, args.chunk)
-    y, u, v = make_frames(400, W4, H4, F4)                     # every rank builds the same sequence, keeps its range
-    lo, hi = F4 * rank // world, F4 * (rank + 1) // world
-    hy, hu, hv = (torch.from_numpy(np.ascontiguousarray(a[lo:hi]).view(np.int16)).pin_memory() for a in (y, u, v))
+    y, u, v = make_frames(400, W4, H4, F4)                     # every rank builds the same sequence, keeps what it needs
+    # Shards: the F4 x 4 (QP, frame) pairs in QP-major order, split evenly over the ranks -- rank r predicts, for one or two
+    # QPs, a contiguous frame range of both components.  (Sharding whole frames with all four QPs leaves 30 frames on 8
+    # GPUs at 4 vs 3.75 frames per rank, a 93.75 % ceiling; 120 pairs split 15 / 15 / ... exactly.)  Every file is still a
+    # concatenation of rank-ordered segments.  --shard frames selects the plain frame ranges.
+    from pmp_vvc_tip2023_b200 import sharding
+
+    def shard_of(r):                                           # [(qp, frame_lo, frame_hi)] of rank r
+        fn = sharding.frame_shards if args.shard == "frames" else sharding.qp_frame_shards
+        return [(QPS[qi], a, b) for qi, a, b in fn(F4, len(QPS), world, r)]
+    pieces = shard_of(rank)
+    f_lo = min([p_[1] for p_ in pieces], default=0)
+    f_hi = max([p_[2] for p_ in pieces], default=0)
+    hy, hu, hv = (torch.from_numpy(np.ascontiguousarray(a[f_lo:f_hi]).view(np.int16)).pin_memory() for a in (y, u, v))
     dy, du, dv = (t.cuda() for t in (hy, hu, hv))
     bh, bw = H4 // 64, W4 // 64
     units = F4 * bh * bw * len(QPS) / 4.0
     keys = [(c, q) for c in COMPS for q in QPS]
+    # consecutive pieces with the same frame range share one predict_frames call (one block cut for all their QPs)
+    calls = sharding.group_calls(pieces)
+    h2d_bytes = sum(2 * (b - a) * (W4 * H4 * 3 // 2) for _, a, b in calls)
 
     def barrier():
         torch.cuda.synchronize()
@@ -361,14 +375,20 @@ def fourk_main(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def predict(ty, tu, tv):
+        res = {}
+        for qs, a, b in calls:
+            res.update(pp.predict_frames(ty[a - f_lo:b - f_lo], tu[a - f_lo:b - f_lo], tv[a - f_lo:b - f_lo], qps=tuple(qs)))
+        return res
+
     def step_device():
-        return pp.predict_frames(dy, du, dv, qps=QPS) if hi > lo else {}
+        return predict(dy, du, dv)
 
     gathered = {}
 
     def step_e2e():
-        res = pp.predict_frames(hy, hu, hv, qps=QPS) if hi > lo else {}
-        texts = {k: (ops.format_text(res[k], handle=pp.handle) if hi > lo else torch.empty(0, dtype=torch.uint8, device="cuda")) for k in keys}
+        res = predict(hy, hu, hv)
+        texts = {k: (ops.format_text(res[k], handle=pp.handle) if k in res else torch.empty(0, dtype=torch.uint8, device="cuda")) for k in keys}
         if world == 1:
             for k in keys:
                 gathered[k] = pp.to_host_pinned(("text",) + k, texts[k], sync=False)     # reusable pinned staging
@@ -415,7 +435,7 @@ def fourk_main(args):
     ms_e2e = timed(step_e2e, args.steps)
     counts = pp.counts()["total"]
     cnt = torch.tensor([counts["blocks"], counts["near_tie_blocks"], counts["near_threshold_blocks"], counts["fp16_saturation_events"],
-                        counts["near_threshold_blocks_tight"]],
+                        counts["near_threshold_blocks_tight"], h2d_bytes],
                        dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(cnt)
@@ -446,10 +466,10 @@ def fourk_main(args):
         assert verified, "sharded PartitionMat bytes differ from the single-GPU result"
     value = units * args.steps / (ms * 1e-3)
     e2e_value = units * args.steps / (ms_e2e * 1e-3)
-    cfg = {"workload": "synthetic 3840x2160 10-bit 4:2:0, 30 frames, ONE sequence, Luma+Chroma x QP 22/27/32/37, frames sharded "
-                       "over %d GPU(s) (BASELINE configs[2])" % world,
+    cfg = {"workload": "synthetic 3840x2160 10-bit 4:2:0, 30 frames, ONE sequence, Luma+Chroma x QP 22/27/32/37, %s sharded "
+                       "over %d GPU(s) (BASELINE configs[2])" % ("(QP, frame) pairs" if args.shard == "frame-qp" else "frames", world),
            "blocks_per_frame": bh * bw, "frames": F4, "qps": list(QPS), "units_per_step": units, "engine": args.engine,
-           "frames_per_rank": [F4 * (r + 1) // world - F4 * r // world for r in range(world)],
+           "shard": args.shard, "qp_frame_ranges_per_rank": [shard_of(r) for r in range(world)],
            "l2": "no flush: per-step working set >> 126 MB L2",
            "weights": "Q nets: reference trained .pkl; MSBD nets: seeded random (trained *_BD_*.pkl absent offline)"}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
@@ -458,7 +478,7 @@ def fourk_main(args):
            "frames_4k_per_s_all_qps": F4 * args.steps / (ms * 1e-3), "frame_qps_4k_per_s": F4 * len(QPS) * args.steps / (ms * 1e-3),
            "gpu_launches": int(launches), "clocks": clocks,
            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                   "h2d_bytes_per_step": int(2 * (y.size + u.size + v.size)), "d2h_bytes_per_step": int(nbytes),
+                   "h2d_bytes_per_step": int(cnt[5]), "d2h_bytes_per_step": int(nbytes),
                    "note": "pinned host frames -> predict -> GPU text formatting -> NCCL gather to rank 0 -> host bytes of the 8 "
                            "PartitionMat files"},
            "file_write": {"ms": 1e3 * t_write, "bytes": int(nbytes), "e2e_plus_write_ctu_per_s": units / (ms_e2e * 1e-3 / args.steps + t_write)},
@@ -486,6 +506,8 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-text-write", action="store_true")
     ap.add_argument("--verify", action="store_true", help="4k30: rank 0 recomputes the whole sequence alone and compares bytes")
+    ap.add_argument("--shard", type=str, default="frame-qp", choices=["frame-qp", "frames"],
+                    help="4k30: shard (QP, frame) pairs evenly over the ranks (default) or whole frame ranges with all QPs")
     ap.add_argument("--out-dir", type=str, default=None, help="4k30 / text_write: where PartitionMat files are written (default: a temp dir)")
     ap.add_argument("--engine", type=str, default="tc", choices=["tc", "simt"])
     ap.add_argument("--chunk", type=int, default=4800)

@@ -119,6 +119,18 @@ def _predict_shard(pred, y, u, v, qps, want_raw=False):
     return texts, times, counts, raw
 
 
+def _predict_pieces(pred, y, u, v, qps, calls, want_raw=False):
+    """One GPU's shard = calls [([qp_index...], frame_lo, frame_hi)] (sharding.group_calls); a GPU holds at most one frame
+    range per QP, so the per-(comp, qp) results of the calls merge without collisions."""
+    texts, times, raw = {}, {}, {}
+    counts = None
+    pred.last_flags = {}            # the decode report below covers exactly this shard's (comp, qp) results
+    for qis, a, b in calls:
+        t, tm, counts, r = _predict_shard(pred, y[a:b], u[a:b], v[a:b], tuple(qps[i] for i in qis), want_raw)
+        texts.update(t); times.update(tm); raw.update(r)        # counts: last_flags accumulates over the calls
+    return texts, times, counts, raw
+
+
 @torch.no_grad()
 def inference_VVC_seqs(args):
     from concurrent.futures import ThreadPoolExecutor
@@ -150,15 +162,23 @@ def inference_VVC_seqs(args):
         t0 = time.time()
         y, u, v = import_yuv420(seq_path, width, height, int(frmnums[seq_id]), ss, is10bit=is10bit)
         nf = y.shape[0]
-        bounds = [nf * g // gpus for g in range(gpus + 1)]
         t_block[s] = time.time() - t0
-        shards = [g for g in range(gpus) if bounds[g + 1] > bounds[g]]
+        # shards: (QP, frame) pairs split evenly over the GPUs (sharding.py); --shard frames = whole frame ranges, all QPs
+        from .sharding import frame_shards, group_calls, qp_frame_shards
+        shard_fn = frame_shards if getattr(args, "shard", "frame-qp") == "frames" else qp_frame_shards
+        pieces = {g: shard_fn(nf, len(qps), gpus, g) for g in range(gpus)}
+        shards = [g for g in range(gpus) if pieces[g]]
         # one worker thread per GPU; .result() re-raises whatever a worker raised (OOM, PmpError, CUDA error): a failed
         # shard must never turn into a silently truncated PartitionMat file
         with ThreadPoolExecutor(max_workers=max(1, len(shards))) as pool:
-            futs = {g: pool.submit(_predict_shard, preds[g], y[bounds[g]:bounds[g + 1]], u[bounds[g]:bounds[g + 1]],
-                                   v[bounds[g]:bounds[g + 1]], qps, getattr(args, "binaryOut", False)) for g in shards}
+            futs = {g: pool.submit(_predict_pieces, preds[g], y, u, v, qps, group_calls(pieces[g]),
+                                   getattr(args, "binaryOut", False)) for g in shards}
             results = {g: f.result() for g, f in futs.items()}
+        # every file must be covered exactly once, in frame order, by the rank-ordered segments of its QP
+        for qi in range(len(qps)):
+            segs = [(a, b) for g in shards for q2, a, b in pieces[g] if q2 == qi]
+            if not segs or segs[0][0] != 0 or segs[-1][1] != nf or any(segs[i][1] != segs[i + 1][0] for i in range(len(segs) - 1)):
+                raise RuntimeError("shards of QP %d do not tile the %d frames: %s" % (qps[qi], nf, segs))
         tot = {"blocks": 0, "near_tie_blocks": 0, "near_threshold_blocks": 0, "near_threshold_blocks_tight": 0,
                "fp16_saturation_events": 0}
         for g in shards:
@@ -179,7 +199,8 @@ def inference_VVC_seqs(args):
                 t0 = time.time()
                 with open(path, "wb") as fp:
                     for g in shards:
-                        fp.write(results[g][0][(comp, qp)])           # KeyError if a shard did not deliver
+                        if any(q2 == qi for q2, _, _ in pieces[g]):
+                            fp.write(results[g][0][(comp, qp)])       # KeyError if a shard did not deliver
                 if getattr(args, "binaryOut", False):
                     # opt-in raw int8 form for the VTM-side binary reader (tools/vtm_reader/pmp_partition_reader.h)
                     from .partition_io import bin_header, values_per_frame
@@ -187,10 +208,12 @@ def inference_VVC_seqs(args):
                     with open(path[:-4] + ".bin", "wb") as fp:
                         fp.write(bin_header(y.shape[0], r_, c_))
                         for g in shards:
-                            fp.write(results[g][3][(comp, qp)])
+                            if any(q2 == qi for q2, _, _ in pieces[g]):
+                                fp.write(results[g][3][(comp, qp)])
                 # shards run concurrently: the sequence's time is the slowest GPU's
-                t_net[s, qi, ci] = max(results[g][1][(comp, qp)][0] for g in shards)
-                t_post[s, qi, ci] = max(results[g][1][(comp, qp)][1] for g in shards) + (time.time() - t0)
+                owners = [g for g in shards if (comp, qp) in results[g][1]]
+                t_net[s, qi, ci] = max(results[g][1][(comp, qp)][0] for g in owners)
+                t_post[s, qi, ci] = max(results[g][1][(comp, qp)][1] for g in owners) + (time.time() - t0)
     log = os.path.join(args.outDir, args.jobID, "Time_Sta_%d_%d.txt" % (args.startSeqID, args.startSeqID + nseq))
     with open(log, "w") as fp:
         for s in range(nseq):
@@ -221,6 +244,8 @@ def build_parser():
     parser.add_argument('--tcDtype', type=str, default='fp16', choices=['fp16', 'bf16'],
                         help='16-bit operand format of the split-precision tensor-core engine')
     parser.add_argument('--nearTol', type=float, default=1e-2, help='tolerance of the near-threshold block count')
+    parser.add_argument('--shard', type=str, default='frame-qp', choices=['frame-qp', 'frames'],
+                        help='multi-GPU work split: (QP, frame) pairs evenly (default) or whole frame ranges with all QPs')
     parser.add_argument('--binaryOut', action='store_true',
                         help='also write <seq>_<comp>_QP<qp>_PartitionMat.bin (raw int8) for tools/vtm_reader')
     return parser

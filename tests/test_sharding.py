@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import decode_ref
-from pmp_vvc_tip2023_b200 import synth
+from pmp_vvc_tip2023_b200 import sharding, synth
 
 
 def shard_bounds(nf, world):
@@ -59,3 +59,23 @@ def test_two_rank_segments_concatenate_to_single_process_file(tmp_path):
     want = decode_ref.partition_text(hor, ver, qtm, dm)
     got = b"".join(open(os.path.join(str(tmp_path), "seg%d.txt" % r), "rb").read() for r in range(world))
     assert got == want
+
+
+def test_qp_frame_shards_cover_each_file_in_rank_order():
+    """(QP, frame) pair sharding: per QP the rank-ordered segments tile [0, nf) exactly, work differs by at most one pair."""
+    for nf in (1, 2, 7, 10, 30, 33):
+        for world in (1, 2, 3, 4, 8):
+            loads = []
+            cover = {qi: [] for qi in range(4)}
+            for r in range(world):
+                pieces = sharding.qp_frame_shards(nf, 4, world, r)
+                loads.append(sum(b - a for _, a, b in pieces))
+                for qi, a, b in pieces:
+                    cover[qi].append((a, b))
+                assert sum(len(qs) * (b - a) for qs, a, b in sharding.group_calls(pieces)) == loads[-1]
+            assert sum(loads) == 4 * nf and max(loads) - min(loads) <= 1
+            for qi, segs in cover.items():
+                assert segs[0][0] == 0 and segs[-1][1] == nf
+                assert all(segs[i][1] == segs[i + 1][0] for i in range(len(segs) - 1))
+    # the plain frame split shares one call between all QPs
+    assert sharding.group_calls(sharding.frame_shards(30, 4, 8, 1)) == [([0, 1, 2, 3], 3, 7)]
