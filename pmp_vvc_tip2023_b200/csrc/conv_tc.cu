@@ -489,6 +489,11 @@ __device__ __forceinline__ void epilogue_process(const TcParams &p, uint32_t tad
     const size_t plane = (size_t)p.H * p.W;
     const size_t pix = (size_t)r * p.W + c;
     const bool mul_early = p.mul.p && !p.res.p;
+    // The tcgen05.ld / wait::ld below are .sync.aligned: the whole warp must arrive together.  A previous call of this
+    // function for the same M-tile ends in a divergent tail (invalid positions return early, the others still store and,
+    // with a residual AND an attention operand, wait for late loads), and nothing forces reconvergence between the two
+    // calls: measured as a hang of 3x3 64->64 @16x16 with both operands (75 % invalid lanes in the last M-tile).
+    __syncwarp();
     float v[CH][8];
     if constexpr (CH <= 2) {
         // pair kernel (CH <= 2 per call, 104 registers): every TMEM load of the call in flight before the one wait
@@ -931,6 +936,7 @@ __device__ __forceinline__ PairGeom pair_geom(const TcParams &p, int item, int r
 }
 
 struct PairBars { uint32_t afull, aempty, wfull, wempty, acc, accempty; };
+constexpr uint32_t TC_PAIR_ISSUED_OFF = 960;     // shared-memory header: uint32 issue tickets per accumulator slot (8 slots)
 
 // MMA issuer of the leader CTA: warp 2+m owns M-tile m of BOTH CTAs' tiles (accumulator buf*4+m).  Measured
 // (tools/stall_prof.py): the issuers spent 85 % of their time executing the issue loop itself, not waiting -- ~200
@@ -939,7 +945,8 @@ struct PairBars { uint32_t afull, aempty, wfull, wempty, acc, accempty; };
 // compile-time constants, every operand warp-uniform so that it lives in uniform registers.
 template <int KW, bool ST>
 __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b, uint32_t tmem_base, uint32_t act_addr,
-                                            uint32_t ring_addr, int m, int cid, int ncl, bool prof, long long t_begin)
+                                            uint32_t ring_addr, int m, int cid, int ncl, bool prof, long long t_begin,
+                                            volatile uint32_t *issued)
 {
     const uint64_t desc_c = ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);                 // SBO 128, version 1
     const uint64_t adesc_c = desc_c | ((uint64_t)(p.plane_bytes >> 4) << 16);                    // LBO = plane stride
@@ -968,7 +975,17 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
         const uint32_t d_tmem = tmem_base + slot * acc_cols;
         if (has_slot) {
             TC_PROF_BEGIN(prof);
+            // With 4 slots and 3 M-tiles per item the slots rotate through the issuers: consecutive uses of a slot belong to
+            // DIFFERENT warps.  A parity wait only tells "the phase before the current one is complete"; an issuer that ran
+            // two uses of the slot ahead of the one that owns the use in between (the epilogue groups drain out of global
+            // order, the weight ring allows one to two items of skew) would see the still-incomplete phase k-2 as "k-1
+            // complete" and overwrite a live accumulator (measured: hang of 3x3 32->64 / 64->64 @16x16 with slow
+            // epilogues).  Issue tickets serialise the uses of a slot: use k waits until the owner of use k-1 has passed its
+            // own wait.  Cycle-free: that owner is behind in the weight ring, never waiting on stages this warp holds.
+            const uint32_t k_use = (idx * MTA + (uint32_t)m) >> (NSLOT == 8u ? 3 : 2);
+            while (issued[slot] < k_use) {}
             mbar_wait(b.accempty + 8 * slot, sph ^ 1u);          // both CTAs drained its previous use
+            if ((threadIdx.x & 31) == 0) issued[slot] = k_use + 1u;
             TC_PROF_END(prof, st_a);
             tc_fence_after();
         }
@@ -1081,6 +1098,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         for (int g = 0; g < p.aslots; g++) { mbar_init(b.afull + 8 * g, 1); mbar_init(b.aempty + 8 * g, TC_MMA_WARPS); }
         for (int s = 0; s < p.nstages; s++) { mbar_init(b.wfull + 8 * s, 1); mbar_init(b.wempty + 8 * s, TC_MMA_WARPS); }
         for (int m = 0; m < p.nslot; m++) { mbar_init(b.acc + 8 * m, 1); mbar_init(b.accempty + 8 * m, 2 * (TC_PAIR_EPI_GROUPS * TC_EPI_WARPS / p.epi_groups)); }
+        for (int m = 0; m < 8; m++) reinterpret_cast<volatile uint32_t *>(smem + TC_PAIR_ISSUED_OFF)[m] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -1162,14 +1180,15 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             // ===== MMA issuers (leader only) =====
             const int m = warp - TC_PAIR_ISSUER_WARP0;
             const uint32_t aa = smem_u32(act), ra = smem_u32(ring);
+            volatile uint32_t *issued = reinterpret_cast<volatile uint32_t *>(smem + TC_PAIR_ISSUED_OFF);
             if (p.stacked) {
-                if (p.kws == 3) pair_issuer<3, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
-                else if (p.kws == 5) pair_issuer<5, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
-                else pair_issuer<1, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
+                if (p.kws == 3) pair_issuer<3, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin, issued);
+                else if (p.kws == 5) pair_issuer<5, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin, issued);
+                else pair_issuer<1, true>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin, issued);
             } else {
-                if (p.kws == 3) pair_issuer<3, false>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
-                else if (p.kws == 5) pair_issuer<5, false>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
-                else pair_issuer<1, false>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin);
+                if (p.kws == 3) pair_issuer<3, false>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin, issued);
+                else if (p.kws == 5) pair_issuer<5, false>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin, issued);
+                else pair_issuer<1, false>(p, b, tmem_base, aa, ra, m, cid, ncl, prof, t_begin, issued);
             }
         }
     } else {

@@ -21,6 +21,18 @@ def test_tc_conv_matches_simt(cfg):
     assert me.value <= (3e-4 if fl & 8 else 2e-5) * max(am.value, 1.0), (me.value, am.value)
 
 
+# Accumulator-slot reuse across issuer warps (round 2): with 4 slots and 3 M-tiles per item (stacked Cout = 64) consecutive
+# uses of a slot belong to different issuer warps; a slow epilogue (residual + attention operand, little MMA work per item)
+# lets one issuer run two uses ahead of another, where a bare parity wait aliases.  These shapes hung before the issue
+# tickets of pair_issuer; several items per cluster are needed (batch >= 1200).
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("cfg", [(64, 64, 3, 16, 1200, 6), (64, 64, 3, 16, 2400, 7), (32, 64, 3, 16, 2400, 3), (32, 64, 3, 16, 2400, 7),
+                                 (64, 64, 3, 8, 2400, 7), (32, 64, 5, 16, 2401, 7)],
+                         ids=lambda c: "cin%d_cout%d_k%d_hw%d_b%d_f%d" % c)
+def test_tc_conv_slow_epilogue_slot_reuse(cfg):
+    test_tc_conv_matches_simt(cfg)
+
+
 # kernel / accumulator-scheme variants (flags: bit 8/9 scheme 1 unstacked 2 stacked, bit 10 CTA-pair kernel, bit 11 force the
 # single-CTA kernel, bits 13..15 cap on the activation buffers), odd batches included (the pair kernel's peer CTA then
 # recomputes the last image and must drop it), batches large enough for several tiles per cluster (ring wrap-around)
