@@ -296,6 +296,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// issuers waiting for a weight stage (they run ahead of the tensor pipe until the ring is exhausted, 25-50 % of their time):
+// build-time A/B knob PMP_ISSUER_BACKOFF=<ns> sleeps between probes instead of spinning
+__device__ __forceinline__ void mbar_wait_issuer(uint32_t bar, uint32_t parity)
+{
+#ifdef PMP_ISSUER_BACKOFF
+    while (!mbar_try_wait(bar, parity)) __nanosleep(PMP_ISSUER_BACKOFF);
+#else
+    while (!mbar_try_wait(bar, parity)) {}
+#endif
+}
 // for the roles that wait long (epilogue for a whole MMA phase, producers for a free slot): back off between probes
 // so the polling does not take issue slots (and power) from the MMA issuers
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
@@ -994,7 +1004,7 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
             { TC_PROF_BEGIN(prof); mbar_wait(b.afull + 8 * as, aph); TC_PROF_END(prof, st_b); }
             uint32_t arow = act16 + as * group16 + (uint32_t)t.qoff;
             for (int kr = 0, sx = 0; kr < KH * RS; kr++) {
-                { TC_PROF_BEGIN(prof); mbar_wait(b.wfull + 8 * s, ph); TC_PROF_END(prof, st_c); }
+                { TC_PROF_BEGIN(prof); mbar_wait_issuer(b.wfull + 8 * s, ph); TC_PROF_END(prof, st_c); }
                 tc_fence_after();
                 const uint64_t ad0 = adesc_c | (uint64_t)(arow + (uint32_t)(sx * KW));
                 const uint64_t bd0 = bdesc_c | (uint64_t)(ring16 + s * row16);
@@ -1032,7 +1042,7 @@ __device__ __forceinline__ void pair_issuer(const TcParams &p, const PairBars &b
         }
         for (int g = 0; g < G2; g++) {           // out += W_sc * x: one slab per group, A = the tile's own positions
             { TC_PROF_BEGIN(prof); mbar_wait(b.afull + 8 * as, aph); TC_PROF_END(prof, st_b); }
-            { TC_PROF_BEGIN(prof); mbar_wait(b.wfull + 8 * s, ph); TC_PROF_END(prof, st_c); }
+            { TC_PROF_BEGIN(prof); mbar_wait_issuer(b.wfull + 8 * s, ph); TC_PROF_END(prof, st_c); }
             tc_fence_after();
             const uint64_t ad = adesc_c | (uint64_t)(act16 + as * group16 + (uint32_t)t.qoff + ctr16);
             const uint64_t bd = bdesc_c | (uint64_t)(ring16 + s * row16);
