@@ -29,8 +29,8 @@ def main():
         wl, wc = pp._wsets[("Luma", 32)], pp._wsets[("Chroma", 32)]
 
         def step():
-            ops.run_component(wl[0], wl[1], True, lb, 1, 1, nb, pp.chunk)
-            ops.run_component(wc[0], wc[1], False, cb, 1, 1, nb, pp.chunk)
+            ops.run_component(wl[0], wl[1], True, lb, 1, 1, nb, pp.chunk, handle=pp.handle)
+            ops.run_component(wc[0], wc[1], False, cb, 1, 1, nb, pp.chunk, handle=pp.handle)
 
         for _ in range(3):
             step()
