@@ -109,6 +109,31 @@ def gen_nets():
 
 
 @torch.no_grad()
+def gen_nets_transplant():
+    """MSBD nets of the UNMODIFIED reference with trained-magnitude weights (synth.transplanted_msbd_state_dict)."""
+    by, bu, bv = cases.net_blocks()
+    xl = torch.from_numpy(by.astype(np.float32)).unsqueeze(1)
+    xc = torch.cat([torch.nn.functional.max_pool2d(xl, 2),
+                    torch.from_numpy(bu.astype(np.float32)).unsqueeze(1),
+                    torch.from_numpy(bv.astype(np.float32)).unsqueeze(1)], 1)
+    res = {}
+    for comp, qp in cases.TRANSPLANT_CASES:
+        x = xl if comp == "Luma" else xc
+        netq = getattr(RefModel, comp + "_Q_Net")()
+        netq.load_state_dict(load_ref_sd(os.path.join(REF, "trained_models", "%s_Q_%d.pkl" % (comp, qp))))
+        netb = getattr(RefModel, comp + "_MSBD_Net")()
+        sdb = synth.transplanted_msbd_state_dict(comp, qp, os.path.join(REF, "trained_models"))
+        netb.load_state_dict({k: torch.from_numpy(v) for k, v in sdb.items()})
+        netq.eval(), netb.eval()
+        qt = netq(x)
+        o0, o1, o2 = netb(x, qt)
+        res["%s_%d_qt" % (comp, qp)] = qt.numpy()
+        res["%s_%d_bd" % (comp, qp)] = torch.stack([o0, o1, o2], 1).numpy()
+        print("nets transplant", comp, qp, float(o2.min()), float(o2.max()))
+    np.savez_compressed(os.path.join(OUT, "nets_transplant_golden.npz"), **res)
+
+
+@torch.no_grad()
 def gen_pipeline():
     """inference_pre_QBD + seq_post_process (file on disk) on a tiny 2-frame sequence."""
     from torch.utils.data import DataLoader, TensorDataset
@@ -158,7 +183,7 @@ def gen_demo_fixture():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["decode", "decode_lamb", "postproc", "nets", "pipeline", "demo"]
+    which = sys.argv[1:] or ["decode", "decode_lamb", "postproc", "nets", "nets_transplant", "pipeline", "demo"]
     if "decode" in which:
         gen_decode()
     if "decode_lamb" in which:
@@ -167,6 +192,8 @@ if __name__ == "__main__":
         gen_postproc()
     if "nets" in which:
         gen_nets()
+    if "nets_transplant" in which:
+        gen_nets_transplant()
     if "pipeline" in which:
         gen_pipeline()
     if "demo" in which:

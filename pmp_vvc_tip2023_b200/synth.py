@@ -122,6 +122,32 @@ def seeded_state_dict(net, seed, gain=0.65):
     return sd
 
 
+def transplanted_msbd_state_dict(comp, qp, model_dir, seed=77):
+    """MSBD weights with TRAINED statistics: every MSBD conv whose shape also occurs in the trained Q nets (Luma and Chroma,
+    this QP; 38 of the 60 conv tensors: 5x5 32->64 / 64->64, 3x3 64->64, 64->32, 32->32, 1x1 shortcuts ...) takes such a
+    trained tensor (cycling through the ones of that shape), the rest stays seeded.  The trained *_BD_*.pkl are absent
+    offline; this gives the MSBD topology activations of trained magnitude (|act| up to ~7e3 at QP 32 / 37 instead of
+    ~2.5e3 with the seeded weights) for the split-precision parity tests.  QP 22 / 27 transplants blow up (not trained for
+    this topology) and are not used."""
+    from .weights import load_reference_pkl
+    import os
+    sd = seeded_state_dict(comp + "_MSBD", seed)
+    pool = {}
+    for c in ("Luma", "Chroma"):
+        q = load_reference_pkl(os.path.join(model_dir, "%s_Q_%d.pkl" % (c, qp)))
+        for _, v in q.items():
+            v = np.asarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v, dtype=np.float32)
+            pool.setdefault(tuple(v.shape), []).append(v)
+    used = {}
+    for name, shp in param_spec(comp + "_MSBD"):
+        shp = tuple(shp)
+        if name.endswith(".weight") and len(shp) == 4 and shp[0] >= 16 and shp in pool:
+            i = used.get(shp, 0)
+            sd[name] = pool[shp][i % len(pool[shp])].copy()
+            used[shp] = i + 1
+    return sd
+
+
 # --------------------------------------------------------------------------
 # structured partition maps for decode-only tests / benches
 # --------------------------------------------------------------------------

@@ -122,3 +122,8 @@ def threshold_distance(qt, bt, dire):
 LAMB_SETS = {"a": (0.6, 0.8, 1.2, 0.4, 0.6), "b": (0.9, 0.5, 2.0, 0.2, 0.8), "c": (0.5, 0.9, 1.0, 0.5, 0.5)}
 LAMB_FAMILIES = ("struct_luma_s15", "struct_chroma_s30", "smooth_luma", "quant_chroma")
 LAMB_BLOCKS = 40
+
+
+# MSBD nets with trained-magnitude weights (synth.transplanted_msbd_state_dict): the (comp, qp) pairs whose transplant
+# stays finite and O(10) at the output
+TRANSPLANT_CASES = [("Luma", 32), ("Luma", 37), ("Chroma", 37)]

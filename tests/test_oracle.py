@@ -92,6 +92,22 @@ def test_nets_oracle_matches_reference(comp, qp):
     assert float((o - ref).abs().max()) < 2e-3 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("comp,qp", cases.TRANSPLANT_CASES)
+def test_msbd_oracle_matches_reference_with_trained_magnitude_weights(comp, qp):
+    """MSBD oracle vs the unmodified reference with transplanted trained weights (activations of trained magnitude)."""
+    g = np.load(os.path.join(GOLDEN, "nets_transplant_golden.npz"))
+    by, bu, bv = cases.net_blocks()
+    luma = comp == "Luma"
+    x = torch.from_numpy(by.astype(np.float32)).unsqueeze(1) if luma else nets_ref.chroma_net_input(by, bu, bv)
+    sdb = {k: torch.from_numpy(v) for k, v in
+           synth.transplanted_msbd_state_dict(comp, qp, os.path.join(ROOT, "trained_models")).items()}
+    with torch.no_grad():
+        o = torch.stack(nets_ref.msbd_net_forward(sdb, x, torch.from_numpy(g["%s_%d_qt" % (comp, qp)]), luma), 1)
+    ref = torch.from_numpy(g["%s_%d_bd" % (comp, qp)])
+    assert float(ref.abs().max()) > 8.0                          # the case is what it claims: outputs of O(10)
+    assert float((o - ref).abs().max()) < 2e-3 * float(ref.abs().max())
+
+
 def test_pipeline_oracle_matches_reference_file():
     """cut_blocks -> nets -> postproc -> decode -> text == the file the reference wrote."""
     g = np.load(os.path.join(GOLDEN, "pipeline_golden.npz"))
