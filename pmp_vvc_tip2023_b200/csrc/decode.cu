@@ -139,17 +139,34 @@ __device__ __forceinline__ i64 fix32(float a)       // |a| -> 2^-32 fixed point 
     return __float2ll_rn(fminf(a, 65536.f) * 4294967296.f);
 }
 
-__device__ __forceinline__ i64 warp_sum64(i64 v)
+// Exact warp sums of non-negative 64-bit values as three 32-bit REDUX.SUM (redux.sync.add) instead of ten SHFL + ten
+// 64-bit adds: limbs narrow enough that 32 lanes cannot overflow 32 bits.
+__device__ __forceinline__ i64 warp_sum64(i64 v)           // v in [0, 2^56): 2^-32 fixed-point error sums of <= 8 cells per lane
 {
+#ifdef PMP_DECODE_SHFL_SUMS
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+#else
+    const u64 u = (u64)v;
+    const unsigned s0 = __reduce_add_sync(0xffffffffu, (unsigned)(u & 0xFFFFFFu));
+    const unsigned s1 = __reduce_add_sync(0xffffffffu, (unsigned)((u >> 24) & 0xFFFFFFu));
+    const unsigned s2 = __reduce_add_sync(0xffffffffu, (unsigned)(u >> 48));          // < 2^8 per lane
+    return (i64)((u64)s0 + ((u64)s1 << 24) + ((u64)s2 << 48));
+#endif
 }
-__device__ __forceinline__ u64 warp_sumu64(u64 v)
+__device__ __forceinline__ u64 warp_sumu64(u64 v)          // six 10-bit counters at bit 0, 10, ..., 50, each <= 8 per lane
 {
+#ifdef PMP_DECODE_SHFL_SUMS
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+#else
+    const unsigned s0 = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0xFFFFFu));
+    const unsigned s1 = __reduce_add_sync(0xffffffffu, (unsigned)((v >> 20) & 0xFFFFFu));
+    const unsigned s2 = __reduce_add_sync(0xffffffffu, (unsigned)(v >> 40));
+    return (u64)s0 + ((u64)s1 << 20) + ((u64)s2 << 40);
+#endif
 }
 
 struct Eval {
